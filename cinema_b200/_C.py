@@ -1,0 +1,310 @@
+"""ctypes binding of libcinema_b200.so -- the only door from Python to the CUDA kernels.
+
+Every wrapper takes torch CUDA tensors, checks dtype / alignment, passes raw device pointers,
+sizes and the current CUDA stream across the C-ABI (include/cinema_b200.h) and raises
+``RuntimeError`` with the library's message on a non-zero status.  There is NO fallback: if the
+shared library is missing or a tensor lives on the CPU the call fails loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcinema_b200.so"
+
+DT_BF16, DT_F32 = 0, 1
+EPI_NONE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
+
+_lib = None
+launches = 0  # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+class KernelLibraryMissing(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "cb_version": (c_int, []),
+    "cb_last_error": (c_char_p, []),
+    "cb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
+                             c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
+                             c_longlong, c_int, c_float, c_int, c_int, c_void_p]),
+    "cb_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "cb_attention_fwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 4
+                         + [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "cb_attention_bwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 5 + [c_void_p]
+                         + [c_void_p, c_longlong, c_longlong, c_longlong] * 3
+                         + [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "cb_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_longlong,
+                                 c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "cb_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong,
+                                 c_void_p, c_void_p, c_void_p]),
+    "cb_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "cb_mask_to_index": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_gather_rows": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p, c_longlong, c_longlong,
+                               c_longlong, c_void_p]),
+    "cb_scatter_rows": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_int, c_int, c_void_p, c_longlong,
+                                c_longlong, c_void_p]),
+    "cb_embed_rows_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_longlong, c_longlong, c_void_p]),
+    "cb_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cb_gather_patches": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "cb_scatter_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cb_masked_mse_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise KernelLibraryMissing(
+                f"{LIB_PATH} not found. cinema_b200 has no CPU / PyTorch fallback: build the CUDA library first "
+                f"(python -m cinema_b200.build, or __graft_entry__.build())."
+            )
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    global launches
+    if rc != 0:
+        raise RuntimeError(f"cinema_b200 {what} failed (status {rc}): {lib().cb_last_error().decode()}")
+    launches += 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("cinema_b200 kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
+    return t.data_ptr()
+
+
+def _ints(vals) -> ctypes.Array:
+    return (c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _lls(vals) -> ctypes.Array:
+    return (c_longlong * len(vals))(*[int(v) for v in vals])
+
+
+def _row_major_2d(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name} must be a 2-D tensor with unit inner stride, got {tuple(t.shape)} {t.stride()}")
+    return t.stride(0)
+
+
+def device_info() -> tuple[int, int, int]:
+    a, b, c = c_int(), c_int(), c_int()
+    _check(lib().cb_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "device_info")
+    return a.value, b.value, c.value
+
+
+# --------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bool = False, b_mn: bool = False,
+         accumulate: bool = False, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
+         residual: torch.Tensor | None = None, aux: torch.Tensor | None = None, epilogue: int = EPI_NONE,
+         alpha: float = 1.0, split_k: int = 0, block_n: int = 0) -> None:
+    """C[M,N] = alpha * A . B^T with the fused epilogue of cb_gemm_bf16 (see include/cinema_b200.h)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    lda, ldb = _row_major_2d(a, "A"), _row_major_2d(b, "B")
+    m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    n, kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if k != kb:
+        raise RuntimeError(f"gemm: contraction mismatch {k} vs {kb}")
+    ref = out if out is not None else out2
+    if tuple(ref.shape) != (m, n):
+        raise RuntimeError(f"gemm: output shape {tuple(ref.shape)} != ({m}, {n})")
+    out_dt = DT_BF16
+    ldo = 0
+    if out is not None:
+        ldo = _row_major_2d(out, "out")
+        out_dt = DT_F32 if out.dtype == torch.float32 else DT_BF16
+        assert out.dtype in (torch.float32, torch.bfloat16)
+    ldo2 = _row_major_2d(out2, "out2") if out2 is not None else 0
+    ldr = _row_major_2d(residual, "residual") if residual is not None else 0
+    ldaux = _row_major_2d(aux, "aux") if aux is not None else 0
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n and bias.is_contiguous()
+    if residual is not None:
+        assert residual.dtype == torch.float32 and tuple(residual.shape) == (m, n)
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and tuple(aux.shape) == (m, n)
+    if out2 is not None:
+        assert out2.dtype == torch.bfloat16
+    _check(lib().cb_gemm_bf16(_ptr(a), lda, int(a_mn), _ptr(b), ldb, int(b_mn), m, n, k, _ptr(out), ldo, out_dt,
+                              int(accumulate), _ptr(out2), ldo2, _ptr(bias), _ptr(residual), ldr, _ptr(aux), ldaux,
+                              epilogue, float(alpha), split_k, block_n, _stream()), "gemm")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[N] (fp32) += column sums of bf16 x[M,N]."""
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and out.numel() == x.shape[1]
+    _check(lib().cb_colsum_bf16(_ptr(x), _row_major_2d(x, "x"), x.shape[0], x.shape[1], _ptr(out), _stream()), "colsum")
+
+
+def _bnh(t: torch.Tensor, name: str) -> tuple[int, int, int, int]:
+    """(ptr, stride_b, stride_n, stride_h) of a (B, N, H, d) bf16 view with unit stride on d."""
+    if t.dim() != 4 or t.stride(3) != 1 or t.dtype != torch.bfloat16:
+        raise RuntimeError(f"{name} must be a bf16 (B, N, H, d) view with unit inner stride")
+    return _ptr(t), t.stride(0), t.stride(1), t.stride(2)
+
+
+def attention_fwd(q, k, v, o, lse, scale: float) -> None:
+    b, nq, h, d = q.shape
+    nk = k.shape[1]
+    assert lse.dtype == torch.float32 and lse.numel() == b * h * nq
+    _check(lib().cb_attention_fwd(*_bnh(q, "q"), *_bnh(k, "k"), *_bnh(v, "v"), *_bnh(o, "o"), _ptr(lse), b, h, nq, nk,
+                                  d, float(scale), _stream()), "attention_fwd")
+
+
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale: float) -> None:
+    b, nq, h, d = q.shape
+    nk = k.shape[1]
+    _check(lib().cb_attention_bwd(*_bnh(q, "q"), *_bnh(k, "k"), *_bnh(v, "v"), *_bnh(o, "o"), *_bnh(do, "do"),
+                                  _ptr(lse), *_bnh(dq, "dq"), *_bnh(dk, "dk"), *_bnh(dv, "dv"), _ptr(delta),
+                                  _ptr(dq_acc), b, h, nq, nk, d, float(scale), _stream()), "attention_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None) -> None:
+    m, d = x.shape
+    assert x.dtype == torch.float32 and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    _check(lib().cb_layernorm_fwd(_ptr(x), _row_major_2d(x, "x"), _ptr(gamma), _ptr(beta), m, d, float(eps),
+                                  _ptr(y16), _row_major_2d(y16, "y16") if y16 is not None else 0,
+                                  _ptr(y32), _row_major_2d(y32, "y32") if y32 is not None else 0,
+                                  _ptr(mean), _ptr(rstd), _stream()), "layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None) -> None:
+    m, d = x.shape
+    dt = DT_BF16 if dy.dtype == torch.bfloat16 else DT_F32
+    assert dy.dtype in (torch.bfloat16, torch.float32) and x.dtype == torch.float32
+    _check(lib().cb_layernorm_bwd(_ptr(dy), _row_major_2d(dy, "dy"), dt, _ptr(x), _row_major_2d(x, "x"), _ptr(mean),
+                                  _ptr(rstd), _ptr(gamma), _ptr(dres),
+                                  _row_major_2d(dres, "dres") if dres is not None else 0, m, d,
+                                  _ptr(dx32), _row_major_2d(dx32, "dx32") if dx32 is not None else 0,
+                                  _ptr(dx16), _row_major_2d(dx16, "dx16") if dx16 is not None else 0,
+                                  _ptr(dgamma), _ptr(dbeta), _stream()), "layernorm_bwd")
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    _check(lib().cb_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast")
+
+
+def mask_to_index(mask: torch.Tensor, n_keep: int):
+    """(B,n) bool mask -> keep_idx (B,n_keep), drop_idx (B,n-n_keep), slot (B,n); all int32, ascending."""
+    assert mask.dtype == torch.bool and mask.dim() == 2 and mask.is_contiguous()
+    b, n = mask.shape
+    keep = torch.empty((b, n_keep), dtype=torch.int32, device=mask.device)
+    drop = torch.empty((b, n - n_keep), dtype=torch.int32, device=mask.device)
+    slot = torch.empty((b, n), dtype=torch.int32, device=mask.device)
+    _check(lib().cb_mask_to_index(_ptr(mask), b, n, n_keep, _ptr(keep), _ptr(drop), _ptr(slot), _stream()),
+           "mask_to_index")
+    return keep, drop, slot
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, out_off: int = 0) -> None:
+    """out[b, out_off+i] = src[b, idx[b,i]] (src (B,n,D) or (n,D)/(1,n,D) broadcast); bit-exact."""
+    b, k = idx.shape
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and src.is_contiguous() and out.is_contiguous()
+    row_bytes = src.shape[-1] * src.element_size()
+    assert out.dtype == src.dtype and out.shape[-1] == src.shape[-1] and out.dim() == 3
+    if src.dim() == 2 or (src.shape[0] == 1 and b > 1):
+        bstride = 0  # one table broadcast over the batch
+    else:
+        assert src.dim() == 3 and src.shape[0] == b
+        bstride = src.shape[1]
+    _check(lib().cb_gather_rows(_ptr(src), bstride, _ptr(idx), b, k, _ptr(out), out.shape[1], out_off, row_bytes,
+                                _stream()), "gather_rows")
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor, src_off: int = 0) -> None:
+    """dst[b, idx[b,i]] = src[b, src_off+i]; rows of dst not listed stay untouched."""
+    b, k = idx.shape
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and src.is_contiguous() and dst.is_contiguous()
+    assert src.dim() == 3 and dst.dim() == 3 and src.dtype == dst.dtype
+    row_bytes = src.shape[-1] * src.element_size()
+    _check(lib().cb_scatter_rows(_ptr(src), src.shape[1], src_off, _ptr(idx), b, k, _ptr(dst), dst.shape[1], row_bytes,
+                                 _stream()), "scatter_rows")
+
+
+def embed_rows(a, a_off: int, row, table, idx, out, out_off: int) -> None:
+    """out[b, out_off+i] = a[b, a_off+i] (opt) + row (opt) + table[idx[b,i]] ; fp32."""
+    b, k = idx.shape
+    d = table.shape[-1]
+    assert table.dtype == torch.float32 and out.dtype == torch.float32 and out.dim() == 3 and out.is_contiguous()
+    assert table.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    if a is not None:
+        assert a.dtype == torch.float32 and a.dim() == 3 and a.is_contiguous()
+    if row is not None:
+        assert row.dtype == torch.float32 and row.numel() == d and row.is_contiguous()
+    _check(lib().cb_embed_rows_f32(_ptr(a), a.shape[1] if a is not None else 0, a_off, _ptr(row), _ptr(table),
+                                   _ptr(idx), b, k, d, _ptr(out), out.shape[1], out_off, _stream()), "embed_rows")
+
+
+def patchify(src: torch.Tensor, dst: torch.Tensor, b: int, c: int, spatial, patch, inverse: bool) -> None:
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+    _check(lib().cb_patchify(_ptr(src), _ptr(dst), b, c, len(spatial), _ints(spatial), _ints(patch),
+                             src.element_size(), int(inverse), _stream()), "patchify")
+
+
+def _src_strides(x: torch.Tensor):
+    return x.stride(0), x.stride(1), [x.stride(i) for i in range(2, x.dim())]
+
+
+def gather_patches(src: torch.Tensor, grid, patch, idx: torch.Tensor | None, chan_last: bool, out: torch.Tensor) -> None:
+    """out rows (bf16) = patches of tokens idx[b,i] of a strided (B,C,*spatial) fp32/bf16 source."""
+    assert src.dtype in (torch.float32, torch.bfloat16) and out.dtype == torch.bfloat16 and out.is_contiguous()
+    sb, sc, ss = _src_strides(src)
+    k = idx.shape[1] if idx is not None else 0
+    if idx is not None:
+        assert idx.dtype == torch.int32 and idx.is_contiguous()
+    _check(lib().cb_gather_patches(_ptr(src), DT_F32 if src.dtype == torch.float32 else DT_BF16, sb, sc, _lls(ss),
+                                   src.shape[0], src.shape[1], len(grid), _ints(grid), _ints(patch), _ptr(idx), k,
+                                   int(chan_last), _ptr(out), _stream()), "gather_patches")
+
+
+def scatter_patches(rows: torch.Tensor, dst: torch.Tensor, grid, patch, idx: torch.Tensor | None, chan_last: bool) -> None:
+    """inverse of gather_patches into a pre-zeroed strided (B,C,*spatial) gradient buffer."""
+    assert rows.is_contiguous() and rows.dtype in (torch.float32, torch.bfloat16)
+    assert dst.dtype in (torch.float32, torch.bfloat16)
+    sb, sc, ss = _src_strides(dst)
+    k = idx.shape[1] if idx is not None else 0
+    dt = lambda t: DT_F32 if t.dtype == torch.float32 else DT_BF16  # noqa: E731
+    _check(lib().cb_scatter_patches(_ptr(rows), dt(rows), _ptr(dst), dt(dst), sb, sc, _lls(ss), dst.shape[0],
+                                    dst.shape[1], len(grid), _ints(grid), _ints(patch), _ptr(idx), k, int(chan_last),
+                                    _stream()), "scatter_patches")
+
+
+def masked_mse_fwd(image, patch, mask, slot, pred, norm_target: bool, eps: float, acc, diff) -> None:
+    assert image.dtype == torch.float32 and image.is_contiguous() and pred.dtype == torch.float32
+    assert pred.is_contiguous() and mask.dtype == torch.bool and mask.is_contiguous() and slot.dtype == torch.int32
+    assert acc.dtype == torch.float32 and acc.numel() >= 8
+    b, c, *spatial = image.shape
+    _check(lib().cb_masked_mse_fwd(_ptr(image), b, c, len(spatial), _ints(spatial), _ints(patch), _ptr(mask),
+                                   _ptr(slot), _ptr(pred), pred.shape[1], int(norm_target), float(eps), _ptr(acc),
+                                   _ptr(diff), _stream()), "masked_mse_fwd")

@@ -1,0 +1,403 @@
+// HBM-bound data-movement kernels of the MAE path: weight cast, mask -> index lists,
+// row gather / scatter, decoder-embedding assembly, N-d patchify / unpatchify, the fused
+// "patchify + visible-token gather", and bias-gradient column sums.
+// All copies are bit-exact; all accesses are coalesced 16-byte vectors where the layout allows.
+#include "../../include/cinema_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_ND = 4;
+
+struct NdGeom {
+  int ndim;
+  int C;
+  int spatial[MAX_ND];
+  int patch[MAX_ND];
+  int grid[MAX_ND];
+  long long sb, sc;            // source batch / channel strides (elements)
+  long long sstride[MAX_ND];   // source spatial strides (elements)
+  int n_tok;                   // prod(grid)
+  int E;                       // prod(patch) * C
+};
+
+// ---------------------------------------------------------------------------------------
+// fp32 -> bf16 flat cast
+// ---------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    reinterpret_cast<uint4*>(dst)[i] =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long i = (n8 << 3) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// mask -> ascending keep / drop index lists (one warp per batch row, ballot compaction)
+// ---------------------------------------------------------------------------------------
+__global__ void mask_to_index_kernel(const unsigned char* __restrict__ mask, int B, int n, int n_keep,
+                                     int* __restrict__ keep_idx, int* __restrict__ drop_idx, int* __restrict__ slot) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const unsigned char* m = mask + (long long)b * n;
+  const int n_drop = n - n_keep;
+  int nk = 0, nd = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int t = base + lane;
+    const bool valid = t < n;
+    const bool removed = valid && m[t] != 0;
+    const unsigned keep_bits = __ballot_sync(0xffffffffu, valid && !removed);
+    const unsigned drop_bits = __ballot_sync(0xffffffffu, removed);
+    const unsigned below = (1u << lane) - 1u;
+    if (valid) {
+      if (!removed) {
+        const int pos = nk + __popc(keep_bits & below);
+        if (pos < n_keep && keep_idx) keep_idx[(long long)b * n_keep + pos] = t;
+        if (slot) slot[(long long)b * n + t] = pos;
+      } else {
+        const int pos = nd + __popc(drop_bits & below);
+        if (pos < n_drop && drop_idx) drop_idx[(long long)b * n_drop + pos] = t;
+        if (slot) slot[(long long)b * n + t] = pos;
+      }
+    }
+    nk += __popc(keep_bits);
+    nd += __popc(drop_bits);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// row gather / scatter by index, 16-byte vectors, one warp per row
+// ---------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void move_rows_kernel(const uint4* __restrict__ src, long long src_bstride, long long src_off,
+                                 const int* __restrict__ idx, int B, int k, uint4* __restrict__ dst,
+                                 long long dst_bstride, long long dst_off, int vec_per_row) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * k) return;
+  const int b = (int)(row / k);
+  const int i = (int)(row - (long long)b * k);
+  const int t = idx[row];
+  long long s_row, d_row;
+  if (!SCATTER) {
+    s_row = b * src_bstride + t;
+    d_row = b * dst_bstride + dst_off + i;
+  } else {
+    s_row = b * src_bstride + src_off + i;
+    d_row = b * dst_bstride + t;
+  }
+  const uint4* s = src + s_row * vec_per_row;
+  uint4* d = dst + d_row * vec_per_row;
+  for (int v = lane; v < vec_per_row; v += 32) d[v] = __ldg(s + v);
+}
+
+__global__ void embed_rows_kernel(const float4* __restrict__ a, long long a_bstride, long long a_off,
+                                  const float4* __restrict__ rowv, const float4* __restrict__ table,
+                                  const int* __restrict__ idx, int B, int k, int vec_per_row, float4* __restrict__ out,
+                                  long long out_bstride, long long out_off) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * k) return;
+  const int b = (int)(row / k);
+  const int i = (int)(row - (long long)b * k);
+  const float4* t = table + (long long)idx[row] * vec_per_row;
+  const float4* ap = a ? a + (b * a_bstride + a_off + i) * vec_per_row : nullptr;
+  float4* o = out + (b * out_bstride + out_off + i) * vec_per_row;
+  for (int v = lane; v < vec_per_row; v += 32) {
+    float4 r = __ldg(t + v);
+    if (ap) {
+      const float4 x = __ldg(ap + v);
+      r.x += x.x, r.y += x.y, r.z += x.z, r.w += x.w;
+    }
+    if (rowv) {
+      const float4 x = __ldg(rowv + v);
+      r.x += x.x, r.y += x.y, r.z += x.z, r.w += x.w;
+    }
+    o[v] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// patchify / unpatchify: one thread per IMAGE element (image side is the contiguous stream)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool INVERSE>
+__global__ void patchify_kernel(const T* __restrict__ src, T* __restrict__ dst, NdGeom g, long long n_per_batch,
+                                long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long b = e / n_per_batch;
+    long long r = e - b * n_per_batch;  // offset inside (C, S1..Sn)
+    int coord[MAX_ND];
+#pragma unroll
+    for (int a = MAX_ND - 1; a >= 0; --a) {
+      if (a < g.ndim) {
+        coord[a] = (int)(r % g.spatial[a]);
+        r /= g.spatial[a];
+      }
+    }
+    const int c = (int)r;
+    int tok = 0, off = 0;
+#pragma unroll
+    for (int a = 0; a < MAX_ND; ++a) {
+      if (a < g.ndim) {
+        tok = tok * g.grid[a] + coord[a] / g.patch[a];
+        off = off * g.patch[a] + coord[a] % g.patch[a];
+      }
+    }
+    const long long t = (b * g.n_tok + tok) * (long long)g.E + (long long)off * g.C + c;
+    if constexpr (!INVERSE)
+      dst[t] = src[e];
+    else
+      dst[e] = src[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// gather patches of selected tokens from a strided source; one thread per output element
+// ---------------------------------------------------------------------------------------
+template <typename TS, typename TR, bool SCATTER>
+__global__ void patches_kernel(TS* __restrict__ img, TR* __restrict__ rows, NdGeom g, const int* __restrict__ idx,
+                               int k, int chan_last, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int pprod = 1;
+#pragma unroll
+  for (int a = 0; a < MAX_ND; ++a)
+    if (a < g.ndim) pprod *= g.patch[a];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long row = e / g.E;
+    const int el = (int)(e - row * g.E);
+    const int b = (int)(row / k);
+    int tok = idx ? idx[row] : (int)(row - (long long)b * k);
+    int c, off;
+    if (chan_last) {
+      c = el % g.C;
+      off = el / g.C;
+    } else {
+      c = el / pprod;
+      off = el - c * pprod;
+    }
+    long long s = b * g.sb + c * g.sc;
+#pragma unroll
+    for (int a = MAX_ND - 1; a >= 0; --a) {
+      if (a < g.ndim) {
+        const int ga = tok % g.grid[a];
+        tok /= g.grid[a];
+        const int oa = off % g.patch[a];
+        off /= g.patch[a];
+        s += (long long)(ga * g.patch[a] + oa) * g.sstride[a];
+      }
+    }
+    if constexpr (!SCATTER)
+      rows[e] = static_cast<TR>(static_cast<float>(img[s]));
+    else
+      img[s] = static_cast<TS>(static_cast<float>(rows[e]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums of a bf16 matrix (bias gradient): block = 8 warps x 64 columns, rows strided
+// ---------------------------------------------------------------------------------------
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ X, long long ldx, int M, int N, float* __restrict__ out,
+                                   int rows_per_block) {
+  __shared__ float2 part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 64 + lane * 2;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float2 v = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(X + (long long)r * ldx + col)));
+      acc.x += v.x, acc.y += v.y;
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < N) {
+    float2 s = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s.x += part[w][lane].x, s.y += part[w][lane].y;
+    atomicAdd(out + col, s.x);
+    atomicAdd(out + col + 1, s.y);
+  }
+}
+
+int fill_geom(NdGeom& g, int C, int ndim, const int* spatial_or_grid, bool is_grid, const int* patch) {
+  CB_CHECK_ARG(ndim >= 1 && ndim <= MAX_ND, "patch geometry: ndim %d not in 1..4", ndim);
+  g.ndim = ndim, g.C = C, g.n_tok = 1, g.E = C;
+  for (int a = 0; a < MAX_ND; ++a) g.spatial[a] = g.patch[a] = g.grid[a] = 1, g.sstride[a] = 0;
+  for (int a = 0; a < ndim; ++a) {
+    CB_CHECK_ARG(patch[a] > 0, "patch size must be positive");
+    g.patch[a] = patch[a];
+    if (is_grid) {
+      g.grid[a] = spatial_or_grid[a];
+      g.spatial[a] = g.grid[a] * patch[a];
+    } else {
+      g.spatial[a] = spatial_or_grid[a];
+      CB_CHECK_ARG(g.spatial[a] % patch[a] == 0, "Input size (%d) cannot be divided by patch size (%d).", g.spatial[a],
+                   patch[a]);
+      g.grid[a] = g.spatial[a] / patch[a];
+    }
+    g.n_tok *= g.grid[a];
+    g.E *= patch[a];
+  }
+  long long s = 1;  // contiguous default strides
+  for (int a = ndim - 1; a >= 0; --a) g.sstride[a] = s, s *= g.spatial[a];
+  g.sc = s, g.sb = s * C;
+  return 0;
+}
+
+inline int blocks_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)cb_sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int cb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return 0;
+  CB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "cast: buffers must be 16-byte aligned");
+  cast_f32_bf16_kernel<<<blocks_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_mask_to_index(const unsigned char* mask, int B, int n, int n_keep, int* keep_idx, int* drop_idx,
+                                int* slot, void* stream) {
+  CB_CHECK_ARG(B > 0 && n > 0 && n_keep >= 0 && n_keep <= n, "mask_to_index: bad sizes B=%d n=%d keep=%d", B, n, n_keep);
+  mask_to_index_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(mask, B, n, n_keep, keep_idx, drop_idx, slot);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_gather_rows(const void* src, long long src_bstride, const int* idx, int B, int k, void* out,
+                              long long out_bstride, long long out_off, long long row_bytes, void* stream) {
+  if (B <= 0 || k <= 0) return 0;
+  CB_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "gather_rows: row_bytes %lld must be a multiple of 16", row_bytes);
+  const long long rows = (long long)B * k;
+  move_rows_kernel<false><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, src_bstride, 0, idx, B, k, (uint4*)out, out_bstride, out_off, (int)(row_bytes / 16));
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_scatter_rows(const void* src, long long src_bstride, long long src_off, const int* idx, int B, int k,
+                               void* dst, long long dst_bstride, long long row_bytes, void* stream) {
+  if (B <= 0 || k <= 0) return 0;
+  CB_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "scatter_rows: row_bytes %lld must be a multiple of 16", row_bytes);
+  const long long rows = (long long)B * k;
+  move_rows_kernel<true><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, src_bstride, src_off, idx, B, k, (uint4*)dst, dst_bstride, 0, (int)(row_bytes / 16));
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, const float* row,
+                                 const float* table, const int* idx, int B, int k, int D, float* out,
+                                 long long out_bstride, long long out_off, void* stream) {
+  if (B <= 0 || k <= 0) return 0;
+  CB_CHECK_ARG(D > 0 && D % 4 == 0, "embed_rows: D=%d must be a multiple of 4", D);
+  const long long rows = (long long)B * k;
+  embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)a, a_bstride, a_off, (const float4*)row, (const float4*)table, idx, B, k, D / 4, (float4*)out,
+      out_bstride, out_off);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_patchify(const void* src, void* dst, int B, int C, int ndim, const int* spatial, const int* patch,
+                           int elem_bytes, int inverse, void* stream) {
+  NdGeom g;
+  if (int rc = fill_geom(g, C, ndim, spatial, false, patch)) return rc;
+  CB_CHECK_ARG(elem_bytes == 2 || elem_bytes == 4, "patchify: element size %d unsupported", elem_bytes);
+  const long long per_batch = g.sb;
+  const long long total = per_batch * B;
+  if (total <= 0) return 0;
+  const int blocks = blocks_for(total, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (elem_bytes == 4) {
+    if (!inverse)
+      patchify_kernel<float, false><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, g, per_batch, total);
+    else
+      patchify_kernel<float, true><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, g, per_batch, total);
+  } else {
+    if (!inverse)
+      patchify_kernel<uint16_t, false><<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
+    else
+      patchify_kernel<uint16_t, true><<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
+  }
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int patches_common(NdGeom& g, long long sb, long long sc, const long long* sstride, int C, int ndim,
+                          const int* grid, const int* patch) {
+  if (int rc = fill_geom(g, C, ndim, grid, true, patch)) return rc;
+  g.sb = sb, g.sc = sc;
+  for (int a = 0; a < ndim; ++a) g.sstride[a] = sstride[a];
+  return 0;
+}
+
+extern "C" int cb_gather_patches(const void* src, int src_dtype, long long sb, long long sc, const long long* sstride,
+                                 int B, int C, int ndim, const int* grid, const int* patch, const int* idx, int k,
+                                 int chan_last, void* out, void* stream) {
+  NdGeom g;
+  if (int rc = patches_common(g, sb, sc, sstride, C, ndim, grid, patch)) return rc;
+  if (idx == nullptr) k = g.n_tok;
+  const long long total = (long long)B * k * g.E;
+  if (total <= 0) return 0;
+  const int blocks = blocks_for(total, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (src_dtype == CB_DT_F32)
+    patches_kernel<const float, bf16, false><<<blocks, 256, 0, s>>>((const float*)src, (bf16*)out, g, idx, k, chan_last, total);
+  else
+    patches_kernel<const bf16, bf16, false><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)out, g, idx, k, chan_last, total);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, int dst_dtype, long long sb, long long sc,
+                                  const long long* sstride, int B, int C, int ndim, const int* grid, const int* patch,
+                                  const int* idx, int k, int chan_last, void* stream) {
+  NdGeom g;
+  if (int rc = patches_common(g, sb, sc, sstride, C, ndim, grid, patch)) return rc;
+  if (idx == nullptr) k = g.n_tok;
+  const long long total = (long long)B * k * g.E;
+  if (total <= 0) return 0;
+  const int blocks = blocks_for(total, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_BF16)
+    patches_kernel<bf16, const bf16, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const bf16*)rows, g, idx, k, chan_last, total);
+  else if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_F32)
+    patches_kernel<float, const bf16, true><<<blocks, 256, 0, s>>>((float*)dst, (const bf16*)rows, g, idx, k, chan_last, total);
+  else if (rows_dtype == CB_DT_F32 && dst_dtype == CB_DT_F32)
+    patches_kernel<float, const float, true><<<blocks, 256, 0, s>>>((float*)dst, (const float*)rows, g, idx, k, chan_last, total);
+  else
+    patches_kernel<bf16, const float, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const float*)rows, g, idx, k, chan_last, total);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_colsum_bf16(const void* X, long long ldx, int M, int N, float* out, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  CB_CHECK_ARG(N % 2 == 0 && ldx % 2 == 0, "colsum: N and ldx must be even");
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (cb_sm_count() * 8 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)X, ldx, M, N, out,
+                                                                                      rows_per_block);
+  CB_LAUNCH_CHECK();
+  return 0;
+}

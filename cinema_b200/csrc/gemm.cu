@@ -1,0 +1,393 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory, persistent warp-specialised CTAs.
+//
+//   C[M,N] = alpha * sum_k A(m,k) * B(n,k)      (+ bias[n]) (GELU / GELU') (+ residual[m,n])
+//
+// Either operand may be K-major (contraction contiguous) or MN-major (its own M/N index
+// contiguous), which is all a Linear layer needs without ever materialising a transpose:
+//   forward  y  = x W^T : A = x  [M,K]   K-major, B = W  [N,K]  K-major
+//   dgrad    dx = dy W  : A = dy [M,N']  K-major, B = W  [N',K'] read MN-major
+//   wgrad    dW = dy^T x: A = dy [T,N']  MN-major, B = x [T,K']  MN-major (split-K over the tokens T,
+//                          fp32 red.global accumulation straight into the gradient buffer)
+// Replaces the cuBLASLt calls behind nn.Linear at cinema/vit.py:472-477, timm Mlp (cinema/vit.py:570-575),
+// cinema/mae/mae.py:395,435-440 and cinema/convvit.py:121,294-298 of the reference.
+//
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..9 epilogue
+// (two warps per TMEM lane quarter, each owning half of the tile's columns).  Two TMEM accumulator
+// stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include "../../include/cinema_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+
+struct GemmArgs {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, splits, kb_per_split, num_kb;
+  void* out;
+  long long ldo;
+  int out_fp32, atomic_add;
+  bf16* out2;
+  long long ldo2;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  const bf16* aux;
+  long long ldaux;
+  int epi;
+  float alpha;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], EPI_WARPS);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int items = tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int tile = item / p.splits;
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_tile * BM + j * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n_tile * BN + j * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_base = a_base + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(a_base + k * 2048, 8192, 1024, UMMA_SW128)
+                                     : umma_smem_desc(a_base + k * 32, 0, 1024, UMMA_SW128);
+            const uint64_t db = B_MN ? umma_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_SW128)
+                                     : umma_smem_desc(b_base + k * 32, 0, 1024, UMMA_SW128);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CHUNKS = COLS_PER_WARP / 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int tile = item / p.splits;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const long long row = (long long)m_tile * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = n_tile * BN + half * COLS_PER_WARP + c * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        if (col0 >= p.N || !row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // groups of 8 columns (N is a multiple of 8)
+          const int col = col0 + g * 8;
+          if (col >= p.N) break;
+          float* x = v + g * 8;
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+            x[0] += b0.x, x[1] += b0.y, x[2] += b0.z, x[3] += b0.w;
+            x[4] += b1.x, x[5] += b1.y, x[6] += b1.z, x[7] += b1.w;
+          }
+          if (p.epi == CB_EPI_GELU) {
+            // pre-activation is rounded to bf16 first (what autocast feeds nn.GELU), saved for backward
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
+            if (p.out != nullptr) {
+              uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                   pack_bf16(x[6], x[7]));
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = gelu_f(x[j]);
+            uint4 o2 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                  pack_bf16(x[6], x[7]));
+            *reinterpret_cast<uint4*>(p.out2 + row * p.ldo2 + col) = o2;
+            continue;
+          }
+          if (p.epi == CB_EPI_GELU_BWD) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + col));
+            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+            x[0] *= gelu_grad_f(a0.x), x[1] *= gelu_grad_f(a0.y), x[2] *= gelu_grad_f(a1.x), x[3] *= gelu_grad_f(a1.y);
+            x[4] *= gelu_grad_f(a2.x), x[5] *= gelu_grad_f(a2.y), x[6] *= gelu_grad_f(a3.x), x[7] *= gelu_grad_f(a3.y);
+          }
+          if (p.residual != nullptr) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col + 4));
+            x[0] += r0.x, x[1] += r0.y, x[2] += r0.z, x[3] += r0.w;
+            x[4] += r1.x, x[5] += r1.y, x[6] += r1.z, x[7] += r1.w;
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+            if (p.atomic_add) {
+              red_add_v4(o, x[0], x[1], x[2], x[3]);
+              red_add_v4(o + 4, x[4], x[5], x[6], x[7]);
+            } else {
+              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+          } else {
+            uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                 pack_bf16(x[6], x[7]));
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+          }
+          if (p.out2 != nullptr) {  // optional bf16 shadow of an fp32 result
+            uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                 pack_bf16(x[6], x[7]));
+            *reinterpret_cast<uint4*>(p.out2 + row * p.ldo2 + col) = o;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN)
+    rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BK, BM, 128);
+  else
+    rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, BK, 128);
+  if (rc) return rc;
+  if (!B_MN)
+    rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, BK, BN, 128);
+  else
+    rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, BK, 128);
+  if (rc) return rc;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
+  const int grid = items < cb_sm_count() ? items : cb_sm_count();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, GemmArgs& p,
+                   cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(A, lda, B, ldb, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true>(A, lda, B, ldb, p, s);
+  if (a_mn && b_mn) return launch<BN, true, true>(A, lda, B, ldb, p, s);
+  return launch<BN, true, false>(A, lda, B, ldb, p, s);
+}
+
+}  // namespace
+
+extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                            int M, int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2,
+                            long long ldo2, const float* bias, const float* residual, long long ldr, const void* aux,
+                            long long ldaux, int epilogue, float alpha, int split_k, int block_n, void* stream) {
+  CB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  CB_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+  CB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B TMA pitch)");
+  CB_CHECK_ARG(out_dtype == CB_DT_BF16 || out_dtype == CB_DT_F32, "gemm: bad out dtype %d", out_dtype);
+  CB_CHECK_ARG(!(accumulate && out_dtype != CB_DT_F32), "gemm: accumulate needs an fp32 output");
+  CB_CHECK_ARG(epilogue >= 0 && epilogue <= CB_EPI_GELU_BWD, "gemm: bad epilogue %d", epilogue);
+  CB_CHECK_ARG(epilogue != CB_EPI_GELU || (out2 != nullptr && out_dtype == CB_DT_BF16),
+               "gemm: GELU epilogue writes bf16 pre-activation to out (optional) and activation to out2");
+  CB_CHECK_ARG(epilogue != CB_EPI_GELU_BWD || aux != nullptr, "gemm: GELU' epilogue needs aux (pre-activation)");
+  CB_CHECK_ARG(out != nullptr || epilogue == CB_EPI_GELU, "gemm: out is null");
+  CB_CHECK_ARG(ldo % 8 == 0 && (out2 == nullptr || ldo2 % 8 == 0) && (residual == nullptr || ldr % 4 == 0) &&
+                   (aux == nullptr || ldaux % 8 == 0),
+               "gemm: epilogue leading dimensions must keep 16-byte row alignment");
+
+  GemmArgs p;
+  p.M = M, p.N = N, p.K = K;
+  p.num_kb = (K + BK - 1) / BK;
+  p.out = out, p.ldo = ldo, p.out_fp32 = out_dtype == CB_DT_F32, p.atomic_add = accumulate;
+  p.out2 = reinterpret_cast<bf16*>(out2), p.ldo2 = ldo2;
+  p.bias = bias, p.residual = residual, p.ldr = ldr;
+  p.aux = reinterpret_cast<const bf16*>(aux), p.ldaux = ldaux;
+  p.epi = epilogue, p.alpha = alpha;
+  p.num_m_tiles = (M + BM - 1) / BM;
+
+  const int sms = cb_sm_count();
+  // pick the tile width that minimises (waves x per-tile time); ties go to the wider tile
+  int bn = block_n;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int c = cands[i];
+      if (c > 64 && N <= c / 2) continue;
+      const long long t = (long long)p.num_m_tiles * ((N + c - 1) / c);
+      const long long waves = (t + sms - 1) / sms;
+      const double cost = (double)waves * (c + 24);  // +24: fixed per-tile overhead in "column" units
+      if (cost < best) best = cost, bn = c;
+    }
+  }
+  p.num_n_tiles = (N + bn - 1) / bn;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int splits = split_k;
+  if (splits <= 0) {
+    splits = 1;
+    if (accumulate && tiles < sms) {  // wgrad-like: few tiles, long contraction -> split K
+      splits = sms / tiles;
+      const int max_splits = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+      if (splits > max_splits) splits = max_splits;
+    }
+  }
+  if (splits > p.num_kb) splits = p.num_kb;
+  CB_CHECK_ARG(splits == 1 || accumulate, "gemm: split-K needs accumulate=1 (fp32 atomics into a zeroed/accumulated out)");
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  CB_CHECK_ARG(p.splits == 1 || (bias == nullptr && residual == nullptr && epilogue == CB_EPI_NONE),
+               "gemm: split-K supports no bias/residual/activation");
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    case 128: return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    default: return dispatch_major<64>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+  }
+}

@@ -1,0 +1,150 @@
+/* cinema_b200 -- C-ABI of the B200 (sm_100a) kernels behind the CineMA MAE-ViT hot path.
+ *
+ * The reference (mathpluscode/CineMA) has no FFI / plugin layer: its hot path is Python
+ * nn.Modules calling ATen / cuBLAS / cuDNN / SDPA.  The drop-in boundary is therefore the
+ * nn.Module API (cinema_b200/*.py mirrors it), and this header is the native layer that
+ * replaces the library calls *below* that API.  Each entry point names the reference call
+ * site(s) (file:line under /root/reference) whose GPU work it takes over.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (torch's caching allocator); nothing is allocated, freed or retained by the library
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync
+ *   - return 0 on success, non-zero on failure (cb_last_error() gives the message);
+ *     nothing throws across the ABI
+ *   - bf16 buffers are `void*` of 2-byte elements; leading dimensions / strides are in
+ *     ELEMENTS unless the name says bytes
+ */
+#ifndef CINEMA_B200_H_
+#define CINEMA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CINEMA_B200_ABI_VERSION 1
+
+enum { CB_DT_BF16 = 0, CB_DT_F32 = 1 };
+enum { CB_EPI_NONE = 0, CB_EPI_GELU = 1, CB_EPI_GELU_BWD = 2 };
+
+/* ---- library ------------------------------------------------------------------------ */
+int cb_version(void);
+const char* cb_last_error(void);
+int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) ----------------------------------------------------- *
+ * C[M,N] = alpha * sum_k A(m,k) B(n,k), fp32 accumulation in tensor memory.
+ *   a_mn_major = 0: A stored [M,K] (row pitch lda)   1: A stored [K,M]
+ *   b_mn_major = 0: B stored [N,K] (row pitch ldb)   1: B stored [K,N]
+ * epilogue (applied in this order): + bias[n]; CB_EPI_GELU (out <- bf16 pre-activation
+ * [may be NULL], out2 <- bf16 GELU); CB_EPI_GELU_BWD (acc *= GELU'(aux[m,n])); + residual[m,n]
+ * (fp32); store to out as bf16 / fp32, or red.add into fp32 out when accumulate=1; out2 (if
+ * given, non-GELU) receives a bf16 copy of the stored value.
+ * split_k: 0 = auto (only ever >1 when accumulate=1).  block_n: 0 = auto, or 64/128/256.
+ * Replaces nn.Linear forward/backward: cinema/vit.py:472-477,498-499,520 (q, kv, proj),
+ * timm Mlp fc1/GELU/fc2 (cinema/vit.py:570-575), cinema/vit.py:294-298,342 (PatchEmbed.proj),
+ * cinema/convvit.py:121,205 (linear), cinema/convvit.py:252,284 (k==s down convs as GEMM),
+ * cinema/mae/mae.py:395,567 (dec_linear), cinema/mae/mae.py:435-440,594 (pred heads). */
+int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                 int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2, long long ldo2,
+                 const float* bias, const float* residual, long long ldr, const void* aux, long long ldaux,
+                 int epilogue, float alpha, int split_k, int block_n, void* stream);
+
+/* column sums of a bf16 [M,N] matrix accumulated (atomically) into fp32 out[N]: bias gradients.
+ * Replaces the reduce kernels autograd runs for nn.Linear bias (same call sites as above). */
+int cb_colsum_bf16(const void* X, long long ldx, int M, int N, float* out, void* stream);
+
+/* ---- fused attention (tcgen05 flash attention) ---------------------------------------- *
+ * O = softmax(Q K^T * scale) V per (batch, head); head_dim in {32, 64}.  Q/K/V/O are bf16 views
+ * addressed as ptr + b*stride_b + token*stride_n + head*stride_h (+ dim), strides in elements,
+ * so the fused [B,N,3,H,d] projection output is consumed in place (no permute copies).
+ * lse[b,h,q] = log-sum-exp of the scaled scores (fp32), kept for the backward.
+ * Replaces F.scaled_dot_product_attention at cinema/vit.py:505-511 and the permutes at :498-500,519. */
+int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, long long q_sh, const void* k, long long k_sb,
+                     long long k_sn, long long k_sh, const void* v, long long v_sb, long long v_sn, long long v_sh,
+                     void* o, long long o_sb, long long o_sn, long long o_sh, float* lse, int B, int H, int Nq, int Nk,
+                     int head_dim, float scale, void* stream);
+/* dQ, dK, dV (bf16, same addressing scheme).  delta[b,h,q] (fp32 scratch, B*H*Nq) and
+ * dq_acc (fp32 scratch, B*H*Nq*head_dim) are caller-provided workspaces. */
+int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, long long q_sh, const void* k, long long k_sb,
+                     long long k_sn, long long k_sh, const void* v, long long v_sb, long long v_sn, long long v_sh,
+                     const void* o, long long o_sb, long long o_sn, long long o_sh, const void* d_o, long long do_sb,
+                     long long do_sn, long long do_sh, const float* lse, void* dq, long long dq_sb, long long dq_sn,
+                     long long dq_sh, void* dk, long long dk_sb, long long dk_sn, long long dk_sh, void* dv,
+                     long long dv_sb, long long dv_sn, long long dv_sh, float* delta, float* dq_acc, int B, int H,
+                     int Nq, int Nk, int head_dim, float scale, void* stream);
+
+/* ---- LayerNorm (row-wise over the last dim, fp32 statistics) -------------------------- *
+ * y = (x - mean) * rstd * gamma + beta.  x fp32 [M,D] (row pitch ldx).  y16 (bf16) and/or y32
+ * (fp32) may be NULL.  mean / rstd (fp32 [M]) may be NULL for inference.
+ * Replaces nn.LayerNorm at cinema/vit.py:549,564,650,738, cinema/convvit.py:254,290 and the
+ * permute+LayerNorm+permute of ConvLayerNorm (cinema/conv.py:169-187) on channel-last rows. */
+int cb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, int M, int D, float eps,
+                     void* y16, long long ldy16, float* y32, long long ldy32, float* mean, float* rstd, void* stream);
+/* dx = LN'(dy) (+ dres if given) -> dx32 (fp32) and optional bf16 copy dx16; dgamma / dbeta are
+ * accumulated with fp32 atomics (may be NULL).  dy is bf16 (dy_dtype=CB_DT_BF16) or fp32. */
+int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, const float* x, long long ldx, const float* mean,
+                     const float* rstd, const float* gamma, const float* dres, long long lddres, int M, int D,
+                     float* dx32, long long lddx32, void* dx16, long long lddx16, float* dgamma, float* dbeta,
+                     void* stream);
+
+/* ---- data movement (bit-exact) --------------------------------------------------------- */
+/* fp32 -> bf16 (round-to-nearest-even) over a flat buffer: the per-step bf16 shadow of the weights. */
+int cb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* (B,n) boolean mask (1 = removed) -> ascending index lists keep_idx (B,n_keep), drop_idx (B,n-n_keep)
+ * and, optionally, slot[b,t] = position of token t inside its list.  Each row must hold exactly
+ * n_keep zeros.  Replaces the nonzero()+index host-sync pairs behind x[~mask] / x[mask] at
+ * cinema/mae/mae.py:98-99,140,550 and cinema/convvit.py:288. */
+int cb_mask_to_index(const unsigned char* mask, int B, int n, int n_keep, int* keep_idx, int* drop_idx, int* slot,
+                     void* stream);
+
+/* out[b, out_off + i, :] = src[b * src_bstride + idx[b,i], :]  for i < k; rows are row_bytes wide
+ * (multiple of 16).  src_bstride (rows) = 0 broadcasts one table over the batch (pos-embed);
+ * out_bstride is the row count of one batch item of `out`.  Pure byte copy. */
+int cb_gather_rows(const void* src, long long src_bstride, const int* idx, int B, int k, void* out,
+                   long long out_bstride, long long out_off, long long row_bytes, void* stream);
+/* inverse: dst[b * dst_bstride + idx[b,i], :] = src[b, src_off + i, :] (rows not listed are untouched). */
+int cb_scatter_rows(const void* src, long long src_bstride, long long src_off, const int* idx, int B, int k, void* dst,
+                    long long dst_bstride, long long row_bytes, void* stream);
+/* out[b, out_off+i, :] = (a ? a[b, a_off+i, :] : 0) + (row ? row[:] : 0) + table[idx[b,i], :]   (fp32, width D)
+ * The decoder embedding: visible tokens + pos[keep], mask_token + pos[drop]
+ * (cinema/mae/mae.py:68-104,179-204) and the encoder's pos-embed add (cinema/convvit.py:205). */
+int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, const float* row, const float* table,
+                      const int* idx, int B, int k, int D, float* out, long long out_bstride, long long out_off,
+                      void* stream);
+
+/* patchify / unpatchify of a contiguous (B, C, S1..Sn) tensor, n in 1..4, element size 2 or 4 bytes:
+ * tokens (B, prod(grid), prod(patch)*C), channel fastest ("nchpwqdr->nhwdpqrc", cinema/vit.py:67-256).
+ * inverse=0: image -> tokens; inverse=1: tokens -> image. */
+int cb_patchify(const void* src, void* dst, int B, int C, int ndim, const int* spatial, const int* patch,
+                int elem_bytes, int inverse, void* stream);
+
+/* tokens of a SUBSET of patches gathered from an arbitrarily strided source, written as bf16 rows:
+ * out[(b,i), e] = src[b*sb + c*sc + sum_a (g_a*p_a + o_a)*s_a], token = idx[b,i] (idx NULL = all tokens),
+ * e ordered (o_1..o_n, c) when chan_last=1 (PatchEmbed / patchify order) or (c, o_1..o_n) when
+ * chan_last=0 (the flattened conv-weight order of a kernel==stride convolution).
+ * src_dtype: CB_DT_F32 or CB_DT_BF16.  This is patchify + x[~mask] fused (cinema/vit.py:338-342 +
+ * cinema/mae/mae.py:550; cinema/convvit.py:284-288). */
+int cb_gather_patches(const void* src, int src_dtype, long long sb, long long sc, const long long* sstride, int B,
+                      int C, int ndim, const int* grid, const int* patch, const int* idx, int k, int chan_last,
+                      void* out, void* stream);
+/* backward of cb_gather_patches: scatters bf16/fp32 rows back into a (pre-zeroed) strided gradient buffer. */
+int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, int dst_dtype, long long sb, long long sc,
+                       const long long* sstride, int B, int C, int ndim, const int* grid, const int* patch,
+                       const int* idx, int k, int chan_last, void* stream);
+
+/* ---- masked-pixel MSE (cinema/mae/mae.py:107-152) fused with the target patchify (:597) --- *
+ * image fp32 contiguous (B,C,S1..Sn); pred fp32 (B,n_drop,E) rows for the tokens drop_idx[b,j];
+ * slot[b,t] from cb_mask_to_index, mask (B,n_tok).  acc (fp32[8], pre-zeroed) receives
+ *   [0] sum (pred-target)^2 over masked patches   [1] sum of per-patch means   [2] sum of per-patch
+ *   unbiased stds   [3] max normalised target   [4] max pred   (3,4 only when norm_target)
+ * diff (fp32, same shape as pred, may be NULL) receives pred - target for the backward. */
+int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, const int* spatial, const int* patch,
+                      const unsigned char* mask, const int* slot, const float* pred, int n_drop, int norm_target,
+                      float eps, float* acc, float* diff, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CINEMA_B200_H_ */
