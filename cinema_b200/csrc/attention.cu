@@ -335,11 +335,432 @@ extern "C" int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, l
   return head_dim == 64 ? launch_fwd<64>(tq, tk, tv, a, s) : launch_fwd<32>(tq, tk, tv, a, s);
 }
 
-extern "C" int cb_attention_bwd(const void*, long long, long long, long long, const void*, long long, long long,
-                                long long, const void*, long long, long long, long long, const void*, long long,
-                                long long, long long, const void*, long long, long long, long long, const float*, void*,
-                                long long, long long, long long, void*, long long, long long, long long, void*,
-                                long long, long long, long long, float*, float*, int, int, int, int, int, float, void*) {
-  cb_set_error("attention_bwd: not built yet");
-  return -1;
+
+// ============================================================================================
+// Backward.  One CTA per (batch, head, 128-key tile); loop over 128-query tiles i:
+//   S^T  = K Q_i^T            (M = keys, N = queries; lanes = keys)       SS, both K-major
+//   dP^T = V dO_i^T                                                        SS, both K-major
+//   P^T  = exp2(S^T * scale*log2e - lse_q * log2e)            \  two warpgroups, one key row per
+//   dS^T = P^T o (dP^T - delta_q) * scale                     /  thread, 64 query columns each
+//   dV  += P^T  dO_i          A = P^T smem (K-major),  B = dO_i tile read MN-major
+//   dK  += dS^T Q_i           A = dS^T smem (K-major), B = Q_i  tile read MN-major
+//   dQ_i = dS   K             A = dS^T smem read MN-major, B = K tile read MN-major
+// dQ_i is drained from TMEM with fp32 red.global.add into dq_acc (summed over key tiles by the
+// atomics) and converted to bf16 by a small follow-up kernel; dK / dV are written once at the end.
+// The same Q_i / dO_i / K smem tiles serve as K-major and as MN-major operands: only the UMMA
+// descriptors differ, nothing is transposed in memory.
+// TMEM: S^T (128) | dP^T (128) | dV (D) | dK (D) | dQ (D).
+// ============================================================================================
+namespace {
+
+constexpr int BWD_THREADS = 320;
+
+struct AttnBwdArgs {
+  const float* lse;
+  const float* delta;
+  float* dq_acc;  // [B, H, Nq, D] fp32, pre-zeroed
+  bf16* dk;
+  long long dk_sb, dk_sn, dk_sh;
+  bf16* dv;
+  long long dv_sb, dv_sn, dv_sh;
+  int B, H, Nq, Nk;
+  float scale, scale_log2;
+};
+
+template <int D>
+struct BwdCfg {
+  static constexpr int ROW_BYTES = D * 2;
+  static constexpr uint64_t SWZ = D == 64 ? UMMA_SW128 : UMMA_SW64;
+  static constexpr int GROUP_BYTES = 8 * ROW_BYTES;
+  static constexpr int TILE_BYTES = 128 * ROW_BYTES;
+  static constexpr int PS_BYTES = 128 * 128 * 2;  // P^T or dS^T, two 64-column chunks of 16 KB
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE_BYTES;
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;        // 2 stages
+  static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES;   // 2 stages
+  static constexpr int OFF_P = OFF_DO + 2 * TILE_BYTES;
+  static constexpr int OFF_DS = OFF_P + PS_BYTES;
+  static constexpr int OFF_VEC = OFF_DS + PS_BYTES;       // lse / delta: [2 stages][2][128] floats
+  static constexpr int OFF_BAR = OFF_VEC + 2 * 2 * 128 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 256 + D, TM_DQ = 256 + 2 * D;
+};
+
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdArgs p) {
+  using C = BwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* dp_full = bars + 6;
+  uint64_t* sdp_free = bars + 7;   // 8 warp arrivals
+  uint64_t* ps_ready = bars + 8;   // 8 warp arrivals
+  uint64_t* mma2_done = bars + 9;
+  uint64_t* dq_free = bars + 10;   // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* vec = reinterpret_cast<float*>(smem + C::OFF_VEC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_q = (p.Nq + 127) / 128;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      for (int i = 0; i < 2; ++i) mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
+      mbar_init(s_full, 1), mbar_init(dp_full, 1), mbar_init(mma2_done, 1);
+      mbar_init(sdp_free, 8), mbar_init(ps_ready, 8), mbar_init(dq_free, 8);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_q), tma_prefetch_desc(&tm_k), tma_prefetch_desc(&tm_v), tma_prefetch_desc(&tm_do);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * C::TILE_BYTES);
+      tma_load_4d(smem + C::OFF_K, &tm_k, kv_full, 0, h, kv0, b);
+      tma_load_4d(smem + C::OFF_V, &tm_v, kv_full, 0, h, kv0, b);
+      for (int i = 0; i < n_q; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[s], 2 * C::TILE_BYTES);
+        tma_load_4d(smem + C::OFF_Q + s * C::TILE_BYTES, &tm_q, &qdo_full[s], 0, h, i * 128, b);
+        tma_load_4d(smem + C::OFF_DO + s * C::TILE_BYTES, &tm_do, &qdo_full[s], 0, h, i * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, D, false, true);  // dV, dK
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, true, true);   // dQ
+      const uint32_t k_base = smem_u32(smem + C::OFF_K);
+      const uint32_t v_base = smem_u32(smem + C::OFF_V);
+      const uint32_t q_base = smem_u32(smem + C::OFF_Q);
+      const uint32_t do_base = smem_u32(smem + C::OFF_DO);
+      const uint32_t p_base = smem_u32(smem + C::OFF_P);
+      const uint32_t ds_base = smem_u32(smem + C::OFF_DS);
+      auto issue_s_dp = [&](int i) {
+        const uint32_t qs = q_base + (i & 1) * C::TILE_BYTES;
+        const uint32_t dos = do_base + (i & 1) * C::TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16_ss(tmem_base + C::TM_S, umma_smem_desc(k_base + kk * 32, 0, C::GROUP_BYTES, C::SWZ),
+                       umma_smem_desc(qs + kk * 32, 0, C::GROUP_BYTES, C::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(s_full);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16_ss(tmem_base + C::TM_DP, umma_smem_desc(v_base + kk * 32, 0, C::GROUP_BYTES, C::SWZ),
+                       umma_smem_desc(dos + kk * 32, 0, C::GROUP_BYTES, C::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tcgen05_fence_after();
+      issue_s_dp(0);
+      for (int i = 0; i < n_q; ++i) {
+        if (i + 1 < n_q) {
+          mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+          mbar_wait(sdp_free, i & 1);  // both warpgroups hold S^T_i / dP^T_i in registers
+          tcgen05_fence_after();
+          issue_s_dp(i + 1);
+        }
+        mbar_wait(ps_ready, i & 1);
+        if (i > 0) mbar_wait(dq_free, (i - 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t qs = q_base + (i & 1) * C::TILE_BYTES;
+        const uint32_t dos = do_base + (i & 1) * C::TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // dV += P^T dO_i
+          const uint64_t da = umma_smem_desc(p_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
+          const uint64_t db = umma_smem_desc(dos + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+          umma_bf16_ss(tmem_base + C::TM_DV, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // dK += dS^T Q_i
+          const uint64_t da = umma_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
+          const uint64_t db = umma_smem_desc(qs + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+          umma_bf16_ss(tmem_base + C::TM_DK, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // dQ_i = dS K   (A = dS^T read MN-major: M = queries contiguous)
+          const uint64_t da = umma_smem_desc(ds_base + kk * 2048, 16384, 1024, UMMA_SW128);
+          const uint64_t db = umma_smem_desc(k_base + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+          umma_bf16_ss(tmem_base + C::TM_DQ, da, db, idesc_dq, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(mma2_done);
+        umma_commit(&qdo_empty[i & 1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ two compute warpgroups
+    const int wg = warp >> 2;                 // query-column half handled by this warpgroup
+    const int r = (warp & 3) * 32 + lane;     // key row inside the tile == TMEM lane
+    const int tid = threadIdx.x;              // 0..255
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* p_smem = smem + C::OFF_P + wg * 16384;
+    uint8_t* ds_smem = smem + C::OFF_DS + wg * 16384;
+    const float* lse_g = p.lse + ((long long)b * p.H + h) * p.Nq;
+    const float* delta_g = p.delta + ((long long)b * p.H + h) * p.Nq;
+    float* dq_g = p.dq_acc + ((long long)b * p.H + h) * p.Nq * D;
+
+    auto drain_dq = [&](int i) {  // dQ tile i: lanes = query rows, this warpgroup takes D/2 columns
+      const int q_row = i * 128 + r;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(lane_addr + C::TM_DQ + wg * (D / 2) + c * 16, v);
+        tmem_ld_wait();
+        if (q_row < p.Nq) {
+          float* dst = dq_g + (long long)q_row * D + wg * (D / 2) + c * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            red_add_v4f(dst + 4 * g, __uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                        __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+    };
+
+    // prefetch of the per-query vectors of tile 0 (thread tid < 128 owns query column tid)
+    float lse_next = INFINITY, delta_next = 0.f;
+    if (tid < 128 && tid < p.Nq) lse_next = lse_g[tid] * LOG2E, delta_next = delta_g[tid];
+
+    for (int i = 0; i < n_q; ++i) {
+      float* lse_s = vec + (i & 1) * 256;
+      float* delta_s = lse_s + 128;
+      if (tid < 128) {
+        lse_s[tid] = lse_next, delta_s[tid] = delta_next;
+        const int qn = (i + 1) * 128 + tid;
+        lse_next = INFINITY, delta_next = 0.f;
+        if (i + 1 < n_q && qn < p.Nq) lse_next = lse_g[qn] * LOG2E, delta_next = delta_g[qn];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      float s[64], dp[64];
+      mbar_wait(s_full, i & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_addr + C::TM_S + wg * 64 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(v[k]);
+      }
+      mbar_wait(dp_full, i & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_addr + C::TM_DP + wg * 64 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dp[c * 32 + k] = __uint_as_float(v[k]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
+
+      uint32_t pk[32], dsk[32];  // packed bf16 P^T and dS^T of this row half
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int q_a = wg * 64 + 2 * c;
+        const float p0 = exp2f(fmaf(s[2 * c], p.scale_log2, -lse_s[q_a]));
+        const float p1 = exp2f(fmaf(s[2 * c + 1], p.scale_log2, -lse_s[q_a + 1]));
+        const float d0 = p0 * (dp[2 * c] - delta_s[q_a]) * p.scale;
+        const float d1 = p1 * (dp[2 * c + 1] - delta_s[q_a + 1]) * p.scale;
+        pk[c] = pack_bf16(p0, p1);
+        dsk[c] = pack_bf16(d0, d1);
+      }
+      if (i > 0) {
+        mbar_wait(mma2_done, (i - 1) & 1);  // P / dS smem reusable, dQ_{i-1} complete
+        tcgen05_fence_after();
+        drain_dq(i - 1);
+      }
+#pragma unroll
+      for (int vcol = 0; vcol < 8; ++vcol) {
+        const uint32_t off = sw128_vec_offset(r, vcol);
+        *reinterpret_cast<uint4*>(p_smem + off) = make_uint4(pk[4 * vcol], pk[4 * vcol + 1], pk[4 * vcol + 2], pk[4 * vcol + 3]);
+        *reinterpret_cast<uint4*>(ds_smem + off) =
+            make_uint4(dsk[4 * vcol], dsk[4 * vcol + 1], dsk[4 * vcol + 2], dsk[4 * vcol + 3]);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ps_ready);
+    }
+    mbar_wait(mma2_done, (n_q - 1) & 1);
+    tcgen05_fence_after();
+    drain_dq(n_q - 1);
+
+    // dK / dV epilogue: lanes = key rows, this warpgroup takes D/2 columns of each
+    const int kv_row = kv0 + r;
+    bf16* dk_ptr = p.dk + (long long)b * p.dk_sb + (long long)kv_row * p.dk_sn + (long long)h * p.dk_sh + wg * (D / 2);
+    bf16* dv_ptr = p.dv + (long long)b * p.dv_sb + (long long)kv_row * p.dv_sn + (long long)h * p.dv_sh + wg * (D / 2);
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t a[16], v[16];
+      tmem_ld_32x32b_x16(lane_addr + C::TM_DK + wg * (D / 2) + c * 16, a);
+      tmem_ld_32x32b_x16(lane_addr + C::TM_DV + wg * (D / 2) + c * 16, v);
+      tmem_ld_wait();
+      if (kv_row < p.Nk) {
+        uint4 w0 = make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                              pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
+        uint4 w1 = make_uint4(pack_bf16(__uint_as_float(a[8]), __uint_as_float(a[9])), pack_bf16(__uint_as_float(a[10]), __uint_as_float(a[11])),
+                              pack_bf16(__uint_as_float(a[12]), __uint_as_float(a[13])), pack_bf16(__uint_as_float(a[14]), __uint_as_float(a[15])));
+        reinterpret_cast<uint4*>(dk_ptr + c * 16)[0] = w0;
+        reinterpret_cast<uint4*>(dk_ptr + c * 16)[1] = w1;
+        uint4 x0 = make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                              pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+        uint4 x1 = make_uint4(pack_bf16(__uint_as_float(v[8]), __uint_as_float(v[9])), pack_bf16(__uint_as_float(v[10]), __uint_as_float(v[11])),
+                              pack_bf16(__uint_as_float(v[12]), __uint_as_float(v[13])), pack_bf16(__uint_as_float(v[14]), __uint_as_float(v[15])));
+        reinterpret_cast<uint4*>(dv_ptr + c * 16)[0] = x0;
+        reinterpret_cast<uint4*>(dv_ptr + c * 16)[1] = x1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[b,h,q] = sum_d O[b,q,h,d] * dO[b,q,h,d]; 8 lanes per (b,q,h) row, 16-byte loads
+template <int D>
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sn, long long o_sh,
+                                  const bf16* __restrict__ d_o, long long do_sb, long long do_sn, long long do_sh,
+                                  float* __restrict__ delta, int B, int H, int Nq) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gid >> 3;
+  const int sub = (int)(gid & 7);
+  const long long total = (long long)B * H * Nq;
+  float acc = 0.f;
+  if (row < total) {
+    const int q = (int)(row % Nq);
+    const int h = (int)((row / Nq) % H);
+    const int b = (int)(row / ((long long)Nq * H));
+    const bf16* op = o + b * o_sb + (long long)q * o_sn + (long long)h * o_sh;
+    const bf16* dp = d_o + b * do_sb + (long long)q * do_sn + (long long)h * do_sh;
+    for (int c = sub * 8; c < D; c += 64) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(op + c));
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(dp + c));
+      const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = unpack_bf16(au[k]), y = unpack_bf16(gu[k]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (row < total && sub == 0) delta[row] = acc;
+}
+
+// dq[b,q,h,:] = bf16(dq_acc[b,h,q,:])
+template <int D>
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long sb, long long sn,
+                                       long long sh, int B, int H, int Nq) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int VPR = D / 8;  // 16-byte output vectors per row
+  const long long row = gid / VPR;
+  const int vcol = (int)(gid % VPR);
+  if (row >= (long long)B * H * Nq) return;
+  const int q = (int)(row % Nq);
+  const int h = (int)((row / Nq) % H);
+  const int b = (int)(row / ((long long)Nq * H));
+  const float4 x = __ldg(reinterpret_cast<const float4*>(acc + row * D + vcol * 8));
+  const float4 y = __ldg(reinterpret_cast<const float4*>(acc + row * D + vcol * 8 + 4));
+  *reinterpret_cast<uint4*>(dq + b * sb + (long long)q * sn + (long long)h * sh + vcol * 8) =
+      make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+}
+
+template <int D>
+int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+               const AttnBwdArgs& a, const bf16* o, long long o_sb, long long o_sn, long long o_sh, const bf16* d_o,
+               long long do_sb, long long do_sn, long long do_sh, float* delta, bf16* dq, long long dq_sb,
+               long long dq_sn, long long dq_sh, cudaStream_t stream) {
+  using C = BwdCfg<D>;
+  const long long rows = (long long)a.B * a.H * a.Nq;
+  attn_delta_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, stream>>>(o, o_sb, o_sn, o_sh, d_o, do_sb, do_sn,
+                                                                             do_sh, delta, a.B, a.H, a.Nq);
+  CB_LAUNCH_CHECK();
+  CB_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)rows * D * sizeof(float), stream));
+  auto kern = attn_bwd_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((a.Nk + 127) / 128, a.H, a.B);
+  kern<<<grid, BWD_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, a);
+  CB_LAUNCH_CHECK();
+  const long long vecs = rows * (D / 8);
+  attn_dq_convert_kernel<D><<<(unsigned)((vecs + 255) / 256), 256, 0, stream>>>(a.dq_acc, dq, dq_sb, dq_sn, dq_sh, a.B,
+                                                                                a.H, a.Nq);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, long long q_sh, const void* k,
+                                long long k_sb, long long k_sn, long long k_sh, const void* v, long long v_sb,
+                                long long v_sn, long long v_sh, const void* o, long long o_sb, long long o_sn,
+                                long long o_sh, const void* d_o, long long do_sb, long long do_sn, long long do_sh,
+                                const float* lse, void* dq, long long dq_sb, long long dq_sn, long long dq_sh, void* dk,
+                                long long dk_sb, long long dk_sn, long long dk_sh, void* dv, long long dv_sb,
+                                long long dv_sn, long long dv_sh, float* delta, float* dq_acc, int B, int H, int Nq,
+                                int Nk, int head_dim, float scale, void* stream) {
+  CB_CHECK_ARG(head_dim == 32 || head_dim == 64, "attention_bwd: head_dim %d not supported (32 or 64)", head_dim);
+  CB_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && Nk > 0, "attention_bwd: empty problem");
+  CB_CHECK_ARG(delta != nullptr && dq_acc != nullptr, "attention_bwd: workspaces missing");
+  CUtensorMap tq, tk, tv, tdo;
+  if (int rc = make_qkv_tmap(&tq, q, q_sb, q_sn, q_sh, B, H, Nq, head_dim, 128)) return rc;
+  if (int rc = make_qkv_tmap(&tk, k, k_sb, k_sn, k_sh, B, H, Nk, head_dim, 128)) return rc;
+  if (int rc = make_qkv_tmap(&tv, v, v_sb, v_sn, v_sh, B, H, Nk, head_dim, 128)) return rc;
+  if (int rc = make_qkv_tmap(&tdo, d_o, do_sb, do_sn, do_sh, B, H, Nq, head_dim, 128)) return rc;
+  AttnBwdArgs a;
+  a.lse = lse, a.delta = delta, a.dq_acc = dq_acc;
+  a.dk = (bf16*)dk, a.dk_sb = dk_sb, a.dk_sn = dk_sn, a.dk_sh = dk_sh;
+  a.dv = (bf16*)dv, a.dv_sb = dv_sb, a.dv_sn = dv_sn, a.dv_sh = dv_sh;
+  a.B = B, a.H = H, a.Nq = Nq, a.Nk = Nk, a.scale = scale, a.scale_log2 = scale * LOG2E;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (head_dim == 64)
+    return launch_bwd<64>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh,
+                          delta, (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
+  return launch_bwd<32>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh, delta,
+                        (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
 }
