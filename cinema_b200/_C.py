@@ -52,12 +52,17 @@ _SIGNATURES = {
     "cb_scatter_rows": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_int, c_int, c_void_p, c_longlong,
                                 c_longlong, c_void_p]),
     "cb_embed_rows_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                  c_void_p, c_longlong, c_longlong, c_void_p]),
+                                  c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
+    "cb_colsum_seg_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cb_scale_cast_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_void_p]),
+    "cb_mae_loss_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cb_gather_patches": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "cb_scatter_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int,
-                                   c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                   c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cb_rope_apply": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p]),
     "cb_masked_mse_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
@@ -252,18 +257,55 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor, src_of
                                  _stream()), "scatter_rows")
 
 
-def embed_rows(a, a_off: int, row, table, idx, out, out_off: int) -> None:
-    """out[b, out_off+i] = a[b, a_off+i] (opt) + row (opt) + table[idx[b,i]] ; fp32."""
-    b, k = idx.shape
-    d = table.shape[-1]
-    assert table.dtype == torch.float32 and out.dtype == torch.float32 and out.dim() == 3 and out.is_contiguous()
-    assert table.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+def embed_rows(a, a_off: int, row, table, idx, b: int, k: int, out=None, out16=None, out_off: int = 0) -> None:
+    """out[b, out_off+i] = a[b, a_off+i] (opt) + row (opt) + table[idx[b,i]] (opt); fp32 math, stored to
+    ``out`` (fp32 (B, n, D)) and / or ``out16`` (bf16, same shape)."""
+    ref = out if out is not None else out16
+    d = ref.shape[-1]
+    assert ref.dim() == 3 and ref.is_contiguous() and ref.shape[0] == b
+    if out is not None:
+        assert out.dtype == torch.float32
+    if out16 is not None:
+        assert out16.dtype == torch.bfloat16 and out16.is_contiguous()
+        assert out is None or out16.shape == out.shape
+    if table is not None:
+        assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[-1] == d
+        assert idx.dtype == torch.int32 and idx.is_contiguous() and tuple(idx.shape) == (b, k)
     if a is not None:
-        assert a.dtype == torch.float32 and a.dim() == 3 and a.is_contiguous()
+        assert a.dtype == torch.float32 and a.dim() == 3 and a.is_contiguous() and a.shape[-1] == d
     if row is not None:
         assert row.dtype == torch.float32 and row.numel() == d and row.is_contiguous()
     _check(lib().cb_embed_rows_f32(_ptr(a), a.shape[1] if a is not None else 0, a_off, _ptr(row), _ptr(table),
-                                   _ptr(idx), b, k, d, _ptr(out), out.shape[1], out_off, _stream()), "embed_rows")
+                                   _ptr(idx) if table is not None else None, b, k, d, _ptr(out), _ptr(out16),
+                                   ref.shape[1], out_off, _stream()), "embed_rows")
+
+
+def colsum_seg(x: torch.Tensor, off: int, k: int, out: torch.Tensor) -> None:
+    """out[D] (fp32) += sum_{b, i<k} x[b, off+i, :] for fp32 x (B, n, D)."""
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous() and out.dtype == torch.float32
+    assert out.numel() == x.shape[-1] and out.is_contiguous() and off + k <= x.shape[1]
+    _check(lib().cb_colsum_seg_f32(_ptr(x), x.shape[1], off, x.shape[0], k, x.shape[-1], _ptr(out), _stream()),
+           "colsum_seg")
+
+
+def scale_cast(src: torch.Tensor, dst: torch.Tensor, scale_dev: torch.Tensor | None = None, scale: float = 1.0) -> None:
+    """dst (bf16) = src (fp32) * scale * scale_dev[0]."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    if scale_dev is not None:
+        assert scale_dev.dtype == torch.float32
+    _check(lib().cb_scale_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _ptr(scale_dev), float(scale), _stream()),
+           "scale_cast")
+
+
+def mae_loss_finalize(acc: torch.Tensor, sq_count, patch_count, out: torch.Tensor, scales: torch.Tensor) -> None:
+    """acc (V, 8) -> out[0] = loss, out[1+5v:6+5v] = per-view metrics, scales[v] = d loss / d diff factor."""
+    v = acc.shape[0]
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and acc.shape[1] == 8
+    assert out.dtype == torch.float32 and out.numel() >= 1 + 5 * v and scales.dtype == torch.float32
+    sq = (c_float * v)(*[float(x) for x in sq_count])
+    pc = (c_float * v)(*[float(x) for x in patch_count])
+    _check(lib().cb_mae_loss_finalize(_ptr(acc), v, sq, pc, _ptr(out), _ptr(scales), _stream()), "mae_loss_finalize")
 
 
 def patchify(src: torch.Tensor, dst: torch.Tensor, b: int, c: int, spatial, patch, inverse: bool) -> None:
@@ -288,8 +330,9 @@ def gather_patches(src: torch.Tensor, grid, patch, idx: torch.Tensor | None, cha
                                    int(chan_last), _ptr(out), _stream()), "gather_patches")
 
 
-def scatter_patches(rows: torch.Tensor, dst: torch.Tensor, grid, patch, idx: torch.Tensor | None, chan_last: bool) -> None:
-    """inverse of gather_patches into a pre-zeroed strided (B,C,*spatial) gradient buffer."""
+def scatter_patches(rows: torch.Tensor, dst: torch.Tensor, grid, patch, idx: torch.Tensor | None, chan_last: bool,
+                    accumulate: bool = False) -> None:
+    """inverse of gather_patches into a strided (B,C,*spatial) gradient buffer (overwrite or accumulate)."""
     assert rows.is_contiguous() and rows.dtype in (torch.float32, torch.bfloat16)
     assert dst.dtype in (torch.float32, torch.bfloat16)
     sb, sc, ss = _src_strides(dst)
@@ -297,7 +340,19 @@ def scatter_patches(rows: torch.Tensor, dst: torch.Tensor, grid, patch, idx: tor
     dt = lambda t: DT_F32 if t.dtype == torch.float32 else DT_BF16  # noqa: E731
     _check(lib().cb_scatter_patches(_ptr(rows), dt(rows), _ptr(dst), dt(dst), sb, sc, _lls(ss), dst.shape[0],
                                     dst.shape[1], len(grid), _ints(grid), _ints(patch), _ptr(idx), k, int(chan_last),
-                                    _stream()), "scatter_patches")
+                                    int(accumulate), _stream()), "scatter_patches")
+
+
+def rope_apply(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """x (B, N, H, d) fp32 / bf16 contiguous, cos / sin (>= N, ro/2) fp32 -> rotated copy."""
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    assert cos.dtype == torch.float32 and sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+    b, n, h, d = x.shape
+    assert cos.shape[0] >= n and cos.shape == sin.shape
+    y = torch.empty_like(x)
+    _check(lib().cb_rope_apply(_ptr(x), _ptr(y), DT_F32 if x.dtype == torch.float32 else DT_BF16, _ptr(cos), _ptr(sin),
+                               b, n, h, d, 2 * cos.shape[1], int(transpose), _stream()), "rope_apply")
+    return y
 
 
 def masked_mse_fwd(image, patch, mask, slot, pred, norm_target: bool, eps: float, acc, diff) -> None:

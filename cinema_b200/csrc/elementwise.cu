@@ -102,17 +102,17 @@ __global__ void move_rows_kernel(const uint4* __restrict__ src, long long src_bs
 __global__ void embed_rows_kernel(const float4* __restrict__ a, long long a_bstride, long long a_off,
                                   const float4* __restrict__ rowv, const float4* __restrict__ table,
                                   const int* __restrict__ idx, int B, int k, int vec_per_row, float4* __restrict__ out,
-                                  long long out_bstride, long long out_off) {
+                                  uint2* __restrict__ out16, long long out_bstride, long long out_off) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * k) return;
   const int b = (int)(row / k);
   const int i = (int)(row - (long long)b * k);
-  const float4* t = table + (long long)idx[row] * vec_per_row;
+  const float4* t = table ? table + (long long)idx[row] * vec_per_row : nullptr;
   const float4* ap = a ? a + (b * a_bstride + a_off + i) * vec_per_row : nullptr;
-  float4* o = out + (b * out_bstride + out_off + i) * vec_per_row;
+  const long long o_row = (b * out_bstride + out_off + i) * vec_per_row;
   for (int v = lane; v < vec_per_row; v += 32) {
-    float4 r = __ldg(t + v);
+    float4 r = t ? __ldg(t + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (ap) {
       const float4 x = __ldg(ap + v);
       r.x += x.x, r.y += x.y, r.z += x.z, r.w += x.w;
@@ -121,7 +121,41 @@ __global__ void embed_rows_kernel(const float4* __restrict__ a, long long a_bstr
       const float4 x = __ldg(rowv + v);
       r.x += x.x, r.y += x.y, r.z += x.z, r.w += x.w;
     }
-    o[v] = r;
+    if (out) out[o_row + v] = r;
+    if (out16) out16[o_row + v] = make_uint2(pack_bf16(r.x, r.y), pack_bf16(r.z, r.w));
+  }
+}
+
+// out[d] += sum over (b, i<k) of X[b*bstride + off + i, d]   (fp32; token / bias style gradients)
+__global__ void colsum_seg_f32_kernel(const float* __restrict__ X, long long bstride, long long off, int B, int k, int D,
+                                      float* __restrict__ out, int rows_per_block) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  const long long total = (long long)B * k;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, total);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const long long b = r / k;
+    const long long i = r - b * k;
+    acc += __ldg(X + (b * bstride + off + i) * D + col);
+  }
+  atomicAdd(out + col, acc);
+}
+
+// dst = bf16(src * scale_host * (scale_dev ? *scale_dev : 1))
+__global__ void scale_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n,
+                                  const float* __restrict__ scale_dev, float scale) {
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(a.x * sc, a.y * sc), pack_bf16(a.z * sc, a.w * sc));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i] * sc);
   }
 }
 
@@ -165,7 +199,7 @@ __global__ void patchify_kernel(const T* __restrict__ src, T* __restrict__ dst, 
 // ---------------------------------------------------------------------------------------
 template <typename TS, typename TR, bool SCATTER>
 __global__ void patches_kernel(TS* __restrict__ img, TR* __restrict__ rows, NdGeom g, const int* __restrict__ idx,
-                               int k, int chan_last, long long total) {
+                               int k, int chan_last, long long total, int accumulate) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   int pprod = 1;
 #pragma unroll
@@ -197,6 +231,8 @@ __global__ void patches_kernel(TS* __restrict__ img, TR* __restrict__ rows, NdGe
     }
     if constexpr (!SCATTER)
       rows[e] = static_cast<TR>(static_cast<float>(img[s]));
+    else if (accumulate)  // patches are disjoint: exactly one thread touches each destination element per call
+      img[s] = static_cast<TS>(static_cast<float>(img[s]) + static_cast<float>(rows[e]));
     else
       img[s] = static_cast<TS>(static_cast<float>(rows[e]));
   }
@@ -227,6 +263,34 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ X, long long ldx, in
     for (int w = 1; w < 8; ++w) s.x += part[w][lane].x, s.y += part[w][lane].y;
     atomicAdd(out + col, s.x);
     atomicAdd(out + col + 1, s.y);
+  }
+}
+
+// NeoX-style rotary embedding over the first `ro` of `d` channels (cinema/rotary.py:12-50):
+//   y[..., j]        = x[j] cos_j - x[j + ro/2] sin_j      j < ro/2
+//   y[..., j + ro/2] = x[j + ro/2] cos_j + x[j] sin_j
+// rows are (b, token, head); cos / sin are (n_tokens, ro/2) fp32 tables.  sin_sign = -1 gives the transpose (backward).
+template <typename T>
+__global__ void rope_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, long long rows, int n_tokens, int H, int d, int ro,
+                            float sin_sign) {
+  const int half = ro >> 1;
+  const long long total = rows * d;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long row = e / d;
+    const int c = (int)(e - row * d);
+    const float v = static_cast<float>(x[e]);
+    if (c >= ro) {
+      y[e] = static_cast<T>(v);
+      continue;
+    }
+    const int tok = (int)((row / H) % n_tokens);
+    const int j = c < half ? c : c - half;
+    const float cs = __ldg(cos_t + (long long)tok * half + j);
+    const float sn = __ldg(sin_t + (long long)tok * half + j) * sin_sign;
+    const float other = static_cast<float>(c < half ? x[e + half] : x[e - half]);
+    y[e] = static_cast<T>(c < half ? v * cs - other * sn : v * cs + other * sn);
   }
 }
 
@@ -302,14 +366,15 @@ extern "C" int cb_scatter_rows(const void* src, long long src_bstride, long long
 }
 
 extern "C" int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, const float* row,
-                                 const float* table, const int* idx, int B, int k, int D, float* out,
+                                 const float* table, const int* idx, int B, int k, int D, float* out, void* out16,
                                  long long out_bstride, long long out_off, void* stream) {
   if (B <= 0 || k <= 0) return 0;
   CB_CHECK_ARG(D > 0 && D % 4 == 0, "embed_rows: D=%d must be a multiple of 4", D);
+  CB_CHECK_ARG(out != nullptr || out16 != nullptr, "embed_rows: no output given");
   const long long rows = (long long)B * k;
   embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)a, a_bstride, a_off, (const float4*)row, (const float4*)table, idx, B, k, D / 4, (float4*)out,
-      out_bstride, out_off);
+      (uint2*)out16, out_bstride, out_off);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -358,16 +423,16 @@ extern "C" int cb_gather_patches(const void* src, int src_dtype, long long sb, l
   const int blocks = blocks_for(total, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (src_dtype == CB_DT_F32)
-    patches_kernel<const float, bf16, false><<<blocks, 256, 0, s>>>((const float*)src, (bf16*)out, g, idx, k, chan_last, total);
+    patches_kernel<const float, bf16, false><<<blocks, 256, 0, s>>>((const float*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
   else
-    patches_kernel<const bf16, bf16, false><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)out, g, idx, k, chan_last, total);
+    patches_kernel<const bf16, bf16, false><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
   CB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, int dst_dtype, long long sb, long long sc,
                                   const long long* sstride, int B, int C, int ndim, const int* grid, const int* patch,
-                                  const int* idx, int k, int chan_last, void* stream) {
+                                  const int* idx, int k, int chan_last, int accumulate, void* stream) {
   NdGeom g;
   if (int rc = patches_common(g, sb, sc, sstride, C, ndim, grid, patch)) return rc;
   if (idx == nullptr) k = g.n_tok;
@@ -376,13 +441,13 @@ extern "C" int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, i
   const int blocks = blocks_for(total, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_BF16)
-    patches_kernel<bf16, const bf16, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const bf16*)rows, g, idx, k, chan_last, total);
+    patches_kernel<bf16, const bf16, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
   else if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_F32)
-    patches_kernel<float, const bf16, true><<<blocks, 256, 0, s>>>((float*)dst, (const bf16*)rows, g, idx, k, chan_last, total);
+    patches_kernel<float, const bf16, true><<<blocks, 256, 0, s>>>((float*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
   else if (rows_dtype == CB_DT_F32 && dst_dtype == CB_DT_F32)
-    patches_kernel<float, const float, true><<<blocks, 256, 0, s>>>((float*)dst, (const float*)rows, g, idx, k, chan_last, total);
+    patches_kernel<float, const float, true><<<blocks, 256, 0, s>>>((float*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
   else
-    patches_kernel<bf16, const float, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const float*)rows, g, idx, k, chan_last, total);
+    patches_kernel<bf16, const float, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -398,6 +463,48 @@ extern "C" int cb_colsum_bf16(const void* X, long long ldx, int M, int N, float*
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
   colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)X, ldx, M, N, out,
                                                                                       rows_per_block);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int B, int k, int D, float* out,
+                                 void* stream) {
+  if (B <= 0 || k <= 0 || D <= 0) return 0;
+  const long long total = (long long)B * k;
+  const int col_blocks = (D + 127) / 128;
+  long long row_blocks = ((long long)cb_sm_count() * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (total + 15) / 16) row_blocks = (total + 15) / 16;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = (int)((total + row_blocks - 1) / row_blocks);
+  row_blocks = (total + rows_per_block - 1) / rows_per_block;
+  colsum_seg_f32_kernel<<<dim3(col_blocks, (unsigned)row_blocks), 128, 0, (cudaStream_t)stream>>>(
+      X, bstride_rows, off, B, k, D, out, rows_per_block);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale,
+                                  void* stream) {
+  if (n <= 0) return 0;
+  CB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "scale_cast: buffers must be 16/8-byte aligned");
+  scale_cast_kernel<<<blocks_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n, scale_dev, scale);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_rope_apply(const void* x, void* y, int dtype, const float* cos_t, const float* sin_t, int B,
+                             int n_tokens, int H, int d, int rotary_dim, int transpose, void* stream) {
+  CB_CHECK_ARG(rotary_dim % 2 == 0 && rotary_dim >= 0, "rope: rotary dim %d must be even", rotary_dim);
+  CB_CHECK_ARG(rotary_dim <= d, "Rotary dim %d is larger than the last dimension of x %d", rotary_dim, d);
+  const long long rows = (long long)B * n_tokens * H;
+  if (rows <= 0 || d <= 0) return 0;
+  const float sgn = transpose ? -1.f : 1.f;
+  const int blocks = blocks_for(rows * d, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CB_DT_F32)
+    rope_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, (float*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
+  else
+    rope_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
   CB_LAUNCH_CHECK();
   return 0;
 }

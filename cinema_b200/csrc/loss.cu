@@ -135,7 +135,50 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
   }
 }
 
+struct FinalizeArgs {
+  int V;
+  float sq_count[8];     // B * n_drop * E per view
+  float patch_count[8];  // B * n_tok per view
+};
+
+// One thread: per-view mean squared error and metrics from the accumulators, the view-averaged loss
+// over the views whose loss is finite (cinema/mae/mae.py:604-608, without the host sync), and the
+// d loss / d pred scale of every view.
+__global__ void mae_loss_finalize_kernel(const float* __restrict__ acc, FinalizeArgs a, float* __restrict__ out,
+                                         float* __restrict__ scales) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float sum = 0.f;
+  int n_fin = 0;
+  for (int v = 0; v < a.V; ++v) {
+    const float* ac = acc + v * 8;
+    const float mse = ac[0] / a.sq_count[v];
+    out[1 + v * 5 + 0] = mse;
+    out[1 + v * 5 + 1] = ac[1] / a.patch_count[v];
+    out[1 + v * 5 + 2] = ac[2] / a.patch_count[v];
+    out[1 + v * 5 + 3] = ac[3];
+    out[1 + v * 5 + 4] = ac[4];
+    if (isfinite(mse)) sum += mse, ++n_fin;
+  }
+  out[0] = n_fin > 0 ? sum / (float)n_fin : __int_as_float(0x7fc00000);
+  for (int v = 0; v < a.V; ++v) {
+    const float mse = out[1 + v * 5 + 0];
+    scales[v] = (isfinite(mse) && n_fin > 0) ? 2.0f / (a.sq_count[v] * (float)n_fin) : 0.f;
+  }
+}
+
 }  // namespace
+
+extern "C" int cb_mae_loss_finalize(const float* acc, int n_views, const float* sq_count, const float* patch_count,
+                                    float* out, float* scales, void* stream) {
+  CB_CHECK_ARG(n_views >= 1 && n_views <= 8, "loss_finalize: n_views %d not in 1..8", n_views);
+  FinalizeArgs a;
+  a.V = n_views;
+  for (int v = 0; v < 8; ++v) a.sq_count[v] = a.patch_count[v] = 1.f;
+  for (int v = 0; v < n_views; ++v) a.sq_count[v] = sq_count[v], a.patch_count[v] = patch_count[v];
+  mae_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, a, out, scales);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, const int* spatial, const int* patch,
                                  const unsigned char* mask, const int* slot, const float* pred, int n_drop,

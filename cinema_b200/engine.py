@@ -1,0 +1,320 @@
+"""Host-side orchestration of the sm_100a kernels: linear / LayerNorm / attention / transformer-block
+forward and hand-written backward chains over 2-D row-major activations.
+
+Precision contract (mirrors what ``torch.autocast("cuda", bf16)`` does to the reference modules,
+SURVEY.md section 3.2): the residual stream is fp32; LayerNorm reads fp32 and its output is consumed
+as bf16; every Linear reads bf16 activations and bf16 weights, accumulates in fp32 (TMEM) and
+emits bf16, except where its result is added to the fp32 residual stream, which is fused into
+the GEMM epilogue; attention runs in bf16 with fp32 softmax statistics.  Weight gradients are
+accumulated in fp32 directly into the flat gradient arena.
+
+Nothing here falls back to torch math: every tensor op is a call into ``cinema_b200._C``.
+torch is used for allocation (caching allocator), views and stream ownership only.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+from cinema_b200 import _C
+from cinema_b200.arena import ParamArena
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------
+@dataclass
+class LinW:
+    """One GEMM operand set: bf16 weight (N, K), fp32 bias (N) and their fp32 gradient targets."""
+
+    w16: torch.Tensor
+    bias: torch.Tensor | None
+    gw: torch.Tensor | None
+    gb: torch.Tensor | None
+
+    @property
+    def n(self) -> int:
+        return self.w16.shape[0]
+
+    @property
+    def k(self) -> int:
+        return self.w16.shape[1]
+
+
+def linw(arena: ParamArena, weight: nn.Parameter, bias: nn.Parameter | None, train: bool) -> LinW:
+    n = weight.shape[0]
+    w16 = arena.w16(weight).view(n, -1)
+    gw = arena.grad_view(weight).view(n, -1) if train and weight.requires_grad else None
+    gb = arena.grad_view(bias) if train and bias is not None and bias.requires_grad else None
+    return LinW(w16, bias.data if bias is not None else None, gw, gb)
+
+
+def linw_fused(arena: ParamArena, weights: list[nn.Parameter], biases: list[nn.Parameter | None], train: bool) -> LinW | None:
+    """Several Linear layers with the same input read as ONE (sum N, K) matrix, if the arena laid them out
+    back to back; ``None`` otherwise (callers then issue one GEMM per layer)."""
+    if any(b is None for b in biases) or not arena.adjacent(weights) or not arena.adjacent(biases):  # type: ignore[arg-type]
+        return None
+    k = weights[0][0].numel()
+    n = sum(w.shape[0] for w in weights)
+    tr_w = [w.requires_grad for w in weights]
+    tr_b = [b.requires_grad for b in biases]  # type: ignore[union-attr]
+    if len(set(tr_w)) != 1 or len(set(tr_b)) != 1:
+        return None
+    return LinW(
+        arena.fused16(weights, (n, k)),
+        arena.fused32(biases, (n,)),  # type: ignore[arg-type]
+        arena.fused_grad(weights, (n, k)) if train and tr_w[0] else None,
+        arena.fused_grad(biases, (n,)) if train and tr_b[0] else None,  # type: ignore[arg-type]
+    )
+
+
+# ------------------------------------------------------------------------------------------
+# linear
+# ------------------------------------------------------------------------------------------
+def linear_fwd(x16: torch.Tensor, w: LinW, *, out_dtype: torch.dtype = BF16, residual: torch.Tensor | None = None,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """y = x W^T + b (+ residual).  x16 (M, K) bf16 -> (M, N) bf16 / fp32."""
+    m = x16.shape[0]
+    if out is None:
+        out = torch.empty((m, w.n), dtype=out_dtype, device=x16.device)
+    _C.gemm(x16, w.w16, out, bias=w.bias, residual=residual)
+    return out
+
+
+def linear_gelu_fwd(x16: torch.Tensor, w: LinW) -> tuple[torch.Tensor, torch.Tensor]:
+    """(pre, act) = (x W^T + b, GELU_erf(pre)), both bf16; pre is kept for the backward."""
+    m = x16.shape[0]
+    pre = torch.empty((m, w.n), dtype=BF16, device=x16.device)
+    act = torch.empty((m, w.n), dtype=BF16, device=x16.device)
+    _C.gemm(x16, w.w16, pre, out2=act, bias=w.bias, epilogue=_C.EPI_GELU)
+    return pre, act
+
+
+def linear_bwd(dy16: torch.Tensor, x16: torch.Tensor | None, w: LinW, *, need_dx: bool = True,
+               gelu_aux: torch.Tensor | None = None, dx_dtype: torch.dtype = BF16,
+               dx_out: torch.Tensor | None = None) -> torch.Tensor | None:
+    """dW += dy^T x, db += colsum(dy), and dx = dy W (optionally * GELU'(gelu_aux), the input's pre-activation)."""
+    if w.gw is not None:
+        _C.gemm(dy16, x16, w.gw, a_mn=True, b_mn=True, accumulate=True)
+    if w.gb is not None:
+        _C.colsum(dy16, w.gb)
+    if not need_dx:
+        return None
+    if dx_out is None:
+        dx_out = torch.empty((dy16.shape[0], w.k), dtype=dx_dtype, device=dy16.device)
+    if gelu_aux is not None:
+        _C.gemm(dy16, w.w16, dx_out, b_mn=True, aux=gelu_aux, epilogue=_C.EPI_GELU_BWD)
+    else:
+        _C.gemm(dy16, w.w16, dx_out, b_mn=True)
+    return dx_out
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------
+@dataclass
+class NormW:
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    gg: torch.Tensor | None
+    gb: torch.Tensor | None
+    eps: float
+
+
+def normw(arena: ParamArena, ln: nn.LayerNorm, train: bool) -> NormW:
+    if ln.weight is None or ln.bias is None:
+        raise NotImplementedError("LayerNorm without affine parameters is not supported by the B200 path")
+    return NormW(ln.weight.data, ln.bias.data,
+                 arena.grad_view(ln.weight) if train and ln.weight.requires_grad else None,
+                 arena.grad_view(ln.bias) if train and ln.bias.requires_grad else None, float(ln.eps))
+
+
+def ln_fwd(x32: torch.Tensor, w: NormW, *, want16: bool = True, want32: bool = False, stats: bool = True,
+           y16: torch.Tensor | None = None):
+    m, d = x32.shape
+    dev = x32.device
+    if want16 and y16 is None:
+        y16 = torch.empty((m, d), dtype=BF16, device=dev)
+    y32 = torch.empty((m, d), dtype=F32, device=dev) if want32 else None
+    mean = torch.empty(m, dtype=F32, device=dev) if stats else None
+    rstd = torch.empty(m, dtype=F32, device=dev) if stats else None
+    _C.layernorm_fwd(x32, w.gamma, w.beta, w.eps, y16=y16, y32=y32, mean=mean, rstd=rstd)
+    return y16, y32, mean, rstd
+
+
+def ln_bwd(dy: torch.Tensor, x32: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, w: NormW, *,
+           dres: torch.Tensor | None = None, want16: bool = True, dx32: torch.Tensor | None = None):
+    """dx = LN'(dy) + dres -> (dx32, dx16).  ``dx32`` may alias ``dres`` (row-local read-then-write)."""
+    m, d = x32.shape
+    if dx32 is None:
+        dx32 = torch.empty((m, d), dtype=F32, device=x32.device)
+    dx16 = torch.empty((m, d), dtype=BF16, device=x32.device) if want16 else None
+    _C.layernorm_bwd(dy, x32, mean, rstd, w.gamma, dres=dres, dx32=dx32, dx16=dx16, dgamma=w.gg, dbeta=w.gb)
+    return dx32, dx16
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def check_head_dim(d: int) -> None:
+    if d not in (32, 64):
+        raise NotImplementedError(
+            f"cinema_b200 attention kernels are built for head_dim 32 and 64 (ViT-B/L encoder, MAE decoder); got {d}")
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
+    """q (B, Nq, H, d), k/v (B, Nk, H, d) strided bf16 views -> o (B, Nq, H, d) bf16 contiguous, lse (B, H, Nq)."""
+    b, nq, h, d = q.shape
+    check_head_dim(d)
+    o = torch.empty((b, nq, h, d), dtype=BF16, device=q.device)
+    lse = torch.empty((b, h, nq), dtype=F32, device=q.device)
+    _C.attention_fwd(q, k, v, o, lse, scale)
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, scale: float) -> None:
+    b, nq, h, d = q.shape
+    delta = torch.empty((b, h, nq), dtype=F32, device=q.device)
+    dq_acc = torch.empty((b, h, nq, d), dtype=F32, device=q.device)
+    _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale)
+
+
+# ------------------------------------------------------------------------------------------
+# transformer block (cinema/vit.py:525-609): x += Attn(LN1(x)[, k]);  x += Mlp(LN2(x))
+# ------------------------------------------------------------------------------------------
+@dataclass
+class BlockW:
+    norm1: NormW
+    norm2: NormW
+    qkv: LinW | None  # fused [q | k | v] projection (self-attention)
+    q: LinW
+    kv: LinW
+    proj: LinW
+    fc1: LinW
+    fc2: LinW
+    n_heads: int
+    scale: float
+
+
+def blockw(arena: ParamArena, blk: nn.Module, train: bool) -> BlockW:
+    at = blk.attn
+    if not isinstance(blk.norm1, nn.LayerNorm) or not isinstance(blk.norm2, nn.LayerNorm):
+        raise NotImplementedError("the B200 block path supports nn.LayerNorm only")
+    if not isinstance(at.q_norm, nn.Identity) or not isinstance(blk.ls1, nn.Identity) or blk.training and (
+            not isinstance(blk.drop_path1, nn.Identity)):
+        raise NotImplementedError("qk_norm / LayerScale / DropPath are not part of the MAE hot path (cinema/vit.py:561-577)")
+    return BlockW(
+        normw(arena, blk.norm1, train), normw(arena, blk.norm2, train),
+        linw_fused(arena, [at.q.weight, at.kv.weight], [at.q.bias, at.kv.bias], train),
+        linw(arena, at.q.weight, at.q.bias, train), linw(arena, at.kv.weight, at.kv.bias, train),
+        linw(arena, at.proj.weight, at.proj.bias, train),
+        linw(arena, blk.mlp.fc1.weight, blk.mlp.fc1.bias, train), linw(arena, blk.mlp.fc2.weight, blk.mlp.fc2.bias, train),
+        at.n_heads, float(at.scale),
+    )
+
+
+def _self_qkv_fwd(h16: torch.Tensor, w: BlockW) -> torch.Tensor:
+    """[q | k | v] = h W_qkv^T: one GEMM when the arena fused the weights, else two into one buffer."""
+    m, d = h16.shape
+    qkv = torch.empty((m, 3 * d), dtype=BF16, device=h16.device)
+    if w.qkv is not None:
+        _C.gemm(h16, w.qkv.w16, qkv, bias=w.qkv.bias)
+    else:
+        _C.gemm(h16, w.q.w16, qkv[:, :d], bias=w.q.bias)
+        _C.gemm(h16, w.kv.w16, qkv[:, d:], bias=w.kv.bias)
+    return qkv
+
+
+def block_fwd(x: torch.Tensor, w: BlockW, b: int, kv: tuple[torch.Tensor, torch.Tensor] | None, save: bool):
+    """x: (B*N, D) fp32.  ``kv``: pre-projected (k, v) views (B, Nk, H, d) for cross-attention, else None.
+    Returns (x_out fp32, saved-for-backward tuple or None)."""
+    m, d = x.shape
+    n = m // b
+    hd = d // w.n_heads
+    h1, _, mean1, rstd1 = ln_fwd(x, w.norm1, stats=save)
+    if kv is None:
+        qkv = _self_qkv_fwd(h1, w)
+        q5 = qkv.view(b, n, 3, w.n_heads, hd)
+        q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
+        qsave = qkv
+    else:
+        q2 = linear_fwd(h1, w.q)
+        q = q2.view(b, n, w.n_heads, hd)
+        k, v = kv
+        qsave = q2
+    o, lse = attn_fwd(q, k, v, w.scale)
+    o2 = o.view(m, d)
+    x1 = linear_fwd(o2, w.proj, out_dtype=F32, residual=x)
+    h2, _, mean2, rstd2 = ln_fwd(x1, w.norm2, stats=save)
+    pre, act = linear_gelu_fwd(h2, w.fc1)
+    x2 = linear_fwd(act, w.fc2, out_dtype=F32, residual=x1)
+    if not save:
+        return x2, None
+    return x2, (x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act)
+
+
+def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
+              kv: tuple[torch.Tensor, torch.Tensor] | None, dkv: tuple[torch.Tensor, torch.Tensor] | None):
+    """Backward of :func:`block_fwd`.  (dx32, dx16) is the gradient of the block output in fp32 and bf16.
+    For cross-attention ``dkv`` are the (dk, dv) views this block's key / value gradients are written to.
+    Returns the (fp32, bf16) gradient of the block input; dx32 is updated in place."""
+    x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act = saved
+    m, d = x.shape
+    n = m // b
+    hd = d // w.n_heads
+    # ---- MLP path
+    dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre)
+    dh2 = linear_bwd(dpre, h2, w.fc1)
+    dx32, dx16 = ln_bwd(dh2, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32)
+    # ---- attention path
+    do2 = linear_bwd(dx16, o2, w.proj)
+    do = do2.view(b, n, w.n_heads, hd)
+    o = o2.view(b, n, w.n_heads, hd)
+    if kv is None:
+        q5 = qsave.view(b, n, 3, w.n_heads, hd)
+        dqkv = torch.empty_like(qsave)
+        d5 = dqkv.view(b, n, 3, w.n_heads, hd)
+        attn_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o, do, lse, d5[:, :, 0], d5[:, :, 1], d5[:, :, 2], w.scale)
+        if w.qkv is not None:
+            dh1 = linear_bwd(dqkv, h1, w.qkv)
+        else:
+            # separate q / kv weights: two dgrads summed through the fp32 accumulate path
+            tmp = torch.zeros((m, d), dtype=F32, device=x.device)
+            for part, lw in ((dqkv[:, :d], w.q), (dqkv[:, d:], w.kv)):
+                if lw.gw is not None:
+                    _C.gemm(part, h1, lw.gw, a_mn=True, b_mn=True, accumulate=True)
+                if lw.gb is not None:
+                    _C.colsum(part, lw.gb)
+                _C.gemm(part, lw.w16, tmp, b_mn=True, accumulate=True)
+            dh1 = tmp
+    else:
+        q = qsave.view(b, n, w.n_heads, hd)
+        dq2 = torch.empty_like(qsave)
+        attn_bwd(q, kv[0], kv[1], o, do, lse, dq2.view(b, n, w.n_heads, hd), dkv[0], dkv[1], w.scale)
+        dh1 = linear_bwd(dq2, h1, w.q)
+    dx32, dx16 = ln_bwd(dh1, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32)
+    return dx32, dx16
+
+
+# ------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------
+_ARANGE_CACHE: dict[tuple, torch.Tensor] = {}
+
+
+def arange_idx(b: int, start: int, k: int, device: torch.device) -> torch.Tensor:
+    """(B, k) int32 index rows [start, start + k): the 'slice' form of the row gather / scatter kernels."""
+    key = (b, start, k, str(device))
+    t = _ARANGE_CACHE.get(key)
+    if t is None:
+        t = torch.arange(start, start + k, dtype=torch.int32, device=device).repeat(b, 1).contiguous()
+        if len(_ARANGE_CACHE) > 256:
+            _ARANGE_CACHE.clear()
+        _ARANGE_CACHE[key] = t
+    return t

@@ -107,12 +107,19 @@ int cb_gather_rows(const void* src, long long src_bstride, const int* idx, int B
 /* inverse: dst[b * dst_bstride + idx[b,i], :] = src[b, src_off + i, :] (rows not listed are untouched). */
 int cb_scatter_rows(const void* src, long long src_bstride, long long src_off, const int* idx, int B, int k, void* dst,
                     long long dst_bstride, long long row_bytes, void* stream);
-/* out[b, out_off+i, :] = (a ? a[b, a_off+i, :] : 0) + (row ? row[:] : 0) + table[idx[b,i], :]   (fp32, width D)
+/* out[b, out_off+i, :] = (a ? a[b, a_off+i, :] : 0) + (row ? row[:] : 0) + (table ? table[idx[b,i], :] : 0)
+ * computed in fp32 (width D) and stored to out (fp32) and / or out16 (bf16), same row addressing.
  * The decoder embedding: visible tokens + pos[keep], mask_token + pos[drop]
  * (cinema/mae/mae.py:68-104,179-204) and the encoder's pos-embed add (cinema/convvit.py:205). */
 int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, const float* row, const float* table,
-                      const int* idx, int B, int k, int D, float* out, long long out_bstride, long long out_off,
+                      const int* idx, int B, int k, int D, float* out, void* out16, long long out_bstride,
+                      long long out_off, void* stream);
+/* out[d] += sum_{b<B, i<k} X[(b*bstride_rows + off + i) * D + d]  (fp32): gradients of cls / mask tokens, i.e.
+ * the backward of the broadcast in cinema/vit.py:672 and cinema/mae/mae.py:98-99. */
+int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int B, int k, int D, float* out,
                       void* stream);
+/* dst[i] = bf16(src[i] * scale * (scale_dev ? *scale_dev : 1)) */
+int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale, void* stream);
 
 /* patchify / unpatchify of a contiguous (B, C, S1..Sn) tensor, n in 1..4, element size 2 or 4 bytes:
  * tokens (B, prod(grid), prod(patch)*C), channel fastest ("nchpwqdr->nhwdpqrc", cinema/vit.py:67-256).
@@ -129,20 +136,35 @@ int cb_patchify(const void* src, void* dst, int B, int C, int ndim, const int* s
 int cb_gather_patches(const void* src, int src_dtype, long long sb, long long sc, const long long* sstride, int B,
                       int C, int ndim, const int* grid, const int* patch, const int* idx, int k, int chan_last,
                       void* out, void* stream);
-/* backward of cb_gather_patches: scatters bf16/fp32 rows back into a (pre-zeroed) strided gradient buffer. */
+/* backward of cb_gather_patches: scatters bf16/fp32 rows back into a strided gradient buffer; accumulate=0
+ * overwrites the touched elements (buffer pre-zeroed by the caller), accumulate=1 adds to them. */
 int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, int dst_dtype, long long sb, long long sc,
                        const long long* sstride, int B, int C, int ndim, const int* grid, const int* patch,
-                       const int* idx, int k, int chan_last, void* stream);
+                       const int* idx, int k, int chan_last, int accumulate, void* stream);
+
+/* Rotary position embedding, standalone contract of cinema/rotary.py:25-50,108-128: x, y (B, n_tokens, H, d)
+ * contiguous (fp32 or bf16), cos / sin (n_tokens, rotary_dim/2) fp32 tables, NeoX half rotation over the first
+ * rotary_dim channels, the rest copied.  transpose=1 applies the inverse rotation (the backward). */
+int cb_rope_apply(const void* x, void* y, int dtype, const float* cos_t, const float* sin_t, int B, int n_tokens,
+                  int H, int d, int rotary_dim, int transpose, void* stream);
 
 /* ---- masked-pixel MSE (cinema/mae/mae.py:107-152) fused with the target patchify (:597) --- *
  * image fp32 contiguous (B,C,S1..Sn); pred fp32 (B,n_drop,E) rows for the tokens drop_idx[b,j];
  * slot[b,t] from cb_mask_to_index, mask (B,n_tok).  acc (fp32[8], pre-zeroed) receives
+ *   (acc[3], acc[4] must be pre-set to -inf when norm_target)
  *   [0] sum (pred-target)^2 over masked patches   [1] sum of per-patch means   [2] sum of per-patch
  *   unbiased stds   [3] max normalised target   [4] max pred   (3,4 only when norm_target)
  * diff (fp32, same shape as pred, may be NULL) receives pred - target for the backward. */
 int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, const int* spatial, const int* patch,
                       const unsigned char* mask, const int* slot, const float* pred, int n_drop, int norm_target,
                       float eps, float* acc, float* diff, void* stream);
+
+/* View-averaged loss and metrics from the accumulators of cb_masked_mse_fwd (acc: n_views x 8 floats).
+ * sq_count[v] = B*n_drop*E, patch_count[v] = B*n_tok (HOST arrays).  out[0] = mean of the finite per-view
+ * losses (NaN if none, cinema/mae/mae.py:604-608 without the host sync); out[1+5v..] = {mse, target_mean,
+ * target_std, normed_target_max, pred_max} of view v; scales[v] = d loss / d (pred - target) factor of view v. */
+int cb_mae_loss_finalize(const float* acc, int n_views, const float* sq_count, const float* patch_count, float* out,
+                         float* scales, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,3 +19,19 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir() -> Path:
     return GOLDEN
+
+
+@pytest.fixture
+def emulated_kernels(monkeypatch):
+    """Replace every ``cinema_b200._C`` wrapper by its plain-torch CPU restatement (tests/emu_c.py) so that the
+    host-side orchestration can be exercised without a GPU.  Test infrastructure only."""
+    from cinema_b200 import _C
+
+    from tests import emu_c
+
+    for name in emu_c.ALL:
+        monkeypatch.setattr(_C, name, getattr(emu_c, name))
+    from cinema_b200 import engine
+
+    monkeypatch.setattr(engine, "check_head_dim", lambda d: None)  # the emulation has no head_dim restriction
+    yield

@@ -237,10 +237,44 @@ def test_embed_rows():
     row = torch.randn(d, device=DEV)
     idx = torch.stack([torch.randperm(n, device=DEV)[:k].sort().values for _ in range(b)]).int()
     out = torch.zeros(b, 5 + k, d, device=DEV)
-    _C.embed_rows(a, 1, None, table, idx, out, 5)
+    _C.embed_rows(a, 1, None, table, idx, b, k, out=out, out_off=5)
     torch.testing.assert_close(out[:, 5:], a[:, 1:] + table[idx.long()], rtol=0, atol=0)
-    _C.embed_rows(None, 0, row, table, idx, out, 5)
+    out16 = torch.zeros(b, 5 + k, d, device=DEV, dtype=torch.bfloat16)
+    _C.embed_rows(None, 0, row, table, idx, b, k, out=out, out16=out16, out_off=5)
     torch.testing.assert_close(out[:, 5:], row + table[idx.long()], rtol=0, atol=0)
+    assert torch.equal(out16[:, 5:], (row + table[idx.long()]).to(torch.bfloat16))
+    # table-less form: plain strided row copy (cls rows)
+    _C.embed_rows(a, 0, None, None, None, b, 1, out=out, out_off=2)
+    assert torch.equal(out[:, 2], a[:, 0])
+
+
+def test_colsum_seg_and_scale_cast():
+    b, n, d = 5, 77, 512
+    x = torch.randn(b, n, d, device=DEV)
+    out = torch.ones(d, device=DEV)
+    _C.colsum_seg(x, 3, 40, out)
+    torch.testing.assert_close(out, 1 + x[:, 3:43].double().sum(dim=(0, 1)).float(), rtol=1e-5, atol=1e-4)
+    out.zero_()
+    _C.colsum_seg(x, 0, 1, out)
+    torch.testing.assert_close(out, x[:, 0].sum(0), rtol=1e-5, atol=1e-5)
+    src = torch.randn(1003, device=DEV)
+    dst = torch.empty(1003, device=DEV, dtype=torch.bfloat16)
+    sc = torch.tensor([0.25], device=DEV)
+    _C.scale_cast(src, dst, sc, 2.0)
+    assert torch.equal(dst, (src * 0.5).to(torch.bfloat16))
+
+
+def test_mae_loss_finalize():
+    acc = torch.tensor([[8.0, 6.0, 3.0, 1.5, 2.5, 0, 0, 0], [float("nan"), 1, 1, 0, 0, 0, 0, 0],
+                        [2.0, 4.0, 2.0, -1.0, -2.0, 0, 0, 0]], device=DEV)
+    out = torch.zeros(16, device=DEV)
+    scales = torch.zeros(3, device=DEV)
+    _C.mae_loss_finalize(acc, [4.0, 2.0, 8.0], [2.0, 1.0, 4.0], out, scales)
+    o = out.cpu()
+    assert o[1] == 2.0 and o[2] == 3.0 and o[3] == 1.5 and o[4] == 1.5 and o[5] == 2.5
+    assert torch.isnan(o[6]) and o[11] == 0.25 and o[12] == 1.0
+    assert o[0] == (2.0 + 0.25) / 2  # the non-finite view is dropped
+    assert scales.cpu().tolist() == [2.0 / (4.0 * 2), 0.0, 2.0 / (8.0 * 2)]
 
 
 def _torch_patchify(image, patch):
