@@ -1,0 +1,367 @@
+"""Benchmark of the MAE pre-training hot path (BASELINE.json: "MAE pretrain volumes/sec (ViT-B, mask 0.75)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--lax 192|256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one optimisation step over one synthetic batch of B frame-sets per GPU (one frame-set =
+one "volume": 1 SAX 192x192x16 + 3 LAX 192x192, BASELINE.json configs[2] at one time frame):
+host->device copy, mask draw, conv stem, ViT encoder on the 25 % visible tokens, cross-attention decoder,
+masked-pixel MSE, full backward, gradient all-reduce (N > 1), global-norm clip and AdamW.
+
+One JSON line is printed by rank 0:
+  value      frame-set volumes/s, whole job, inputs resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e        the same through the public API with pinned HOST buffers: H2D copy of every batch and a D2H read of
+             every step's loss inside the timed region
+  roofline   the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, measured live in an
+             instrumented step, against the measured bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU port of the reference path, fp32, torch threads = host cores) on a bounded sample
+``--impl reference`` times that CPU path alone (the reference is pure Python + torch).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+VIEWS = ("sax", "lax_2c", "lax_3c", "lax_4c")
+
+
+# ------------------------------------------------------------------------------------------
+# workload description and algorithmic FLOPs (SURVEY.md section 8d / BASELINE.md section 3)
+# ------------------------------------------------------------------------------------------
+def model_kwargs(size: str, sax, lax) -> dict:
+    dims = {"base": (768, 12, 12), "large": (1024, 24, 16)}[size]
+    return dict(
+        image_size_dict={"sax": tuple(sax), **{v: tuple(lax) for v in VIEWS[1:]}},
+        in_chans_dict={v: 1 for v in VIEWS},
+        enc_patch_size_dict={"sax": (4, 4, 1), **{v: (4, 4) for v in VIEWS[1:]}},
+        enc_scale_factor_dict={"sax": (2, 2, 1), **{v: (2, 2) for v in VIEWS[1:]}},
+        enc_conv_chans=[64, 128], enc_conv_n_blocks=2,
+        enc_embed_dim=dims[0], enc_depth=dims[1], enc_n_heads=dims[2], dec_embed_dim=512, dec_depth=8, dec_n_heads=16,
+    )
+
+
+def train_gflop_per_sample(kw: dict, ratio: float = 0.75) -> dict:
+    """Forward multiply-add = 2 FLOPs; train = 3 x forward; recompute not credited."""
+    d, le, dd, ld = kw["enc_embed_dim"], kw["enc_depth"], kw["dec_embed_dim"], kw["dec_depth"]
+    n_tok, n_keep, conv = [], [], 0.0
+    for v, size in kw["image_size_dict"].items():
+        nd = len(size)
+        eff = [a * b * b for a, b in zip(kw["enc_patch_size_dict"][v], kw["enc_scale_factor_dict"][v])]
+        grid = [s // e for s, e in zip(size, eff)]
+        n = math.prod(grid)
+        n_tok.append(n)
+        n_keep.append(int(n * (1 - ratio)))
+        pos, cin, ps = list(size), 1, kw["enc_patch_size_dict"][v]
+        for lvl, ch in enumerate(kw["enc_conv_chans"]):
+            pos = [s // p for s, p in zip(pos, ps)]
+            p = math.prod(pos)
+            conv += 2 * p * ch * cin * math.prod(ps)                      # strided patch conv
+            conv += kw["enc_conv_n_blocks"] * (2 * p * ch * ch * 10 + 2 * p * ch * 5 ** nd)  # 1x1 x2, mlp 4x x2, dw 5^nd
+            k = [s // g for s, g in zip(pos, grid)]
+            conv += 2 * n * d * ch * math.prod(k)                         # fusion conv over all tokens
+            cin, ps = ch, kw["enc_scale_factor_dict"][v]
+    n_enc = 1 + sum(n_keep)
+    n_k = sum(n_keep)
+    n_q = 1 + sum(n_tok) - n_k
+    enc = le * (24 * n_enc * d * d + 4 * n_enc * n_enc * d)
+    dec = ld * (2 * dd * dd * (10 * n_q + 2 * n_k) + 4 * n_q * n_k * dd)
+    other = sum(2 * n * (512 * d + d * d) for n in n_tok) + 2 * n_enc * d * dd + 2 * (n_q - 1) * dd * 256
+    fwd = enc + dec + other + conv
+    return dict(fwd_gflop=fwd / 1e9, train_gflop=3 * fwd / 1e9, enc_tokens=n_enc, q_tokens=n_q, kv_tokens=n_k,
+                attn_fwd_gflop=(le * 4 * n_enc * n_enc * d + ld * 4 * n_q * n_k * dd) / 1e9)
+
+
+def measured_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synthetic_batch(kw: dict, b: int, seed: int, pin: bool) -> dict:
+    """Images in [0, 1) like ScaleIntensityd (cinema/mae/pretrain.py:184)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {v: torch.rand(b, 1, *s, generator=g) for v, s in kw["image_size_dict"].items()}
+    return {k: t.pin_memory() for k, t in out.items()} if pin else out
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference path) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_throughput(kw: dict, sample_b: int, steps: int, warmup: int) -> dict:
+    from oracle import cinema_oracle as oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = oracle.MAEConfig(**kw)
+    sd = oracle.init_state_dict(cfg, seed=0)
+    batch = synthetic_batch(kw, sample_b, seed=0, pin=False)
+    torch.manual_seed(0)
+    masks = {v: oracle.random_patch_mask(sample_b, cfg.n_patches(v), 0.75) for v in kw["image_size_dict"]}
+    for _ in range(warmup):
+        oracle.train_step_cpu(sd, cfg, batch, masks)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.train_step_cpu(sd, cfg, batch, masks)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": sample_b / dt, "unit": "frame-set volumes/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} forward+backward steps of {sample_b} frame-sets (same views / sizes / ViT-B, fp32, "
+                      f"torch {torch.__version__} CPU, {cores} threads), {dt:.2f} s per step", "ms_per_step": dt * 1e3}
+
+
+# ------------------------------------------------------------------------------------------
+# per-kernel instrumentation (one eager step, CUDA events around every C-ABI launch)
+# ------------------------------------------------------------------------------------------
+def instrumented_step(trainer, batch_dev: dict) -> dict:
+    from cinema_b200 import _C
+
+    records: list[tuple[str, float, torch.cuda.Event, torch.cuda.Event]] = []
+    originals = {}
+
+    def flops_of(name, args, kwargs) -> float:
+        if name == "gemm":
+            a, b = args[0], args[1]
+            m, k = (a.shape[1], a.shape[0]) if kwargs.get("a_mn") else (a.shape[0], a.shape[1])
+            n = b.shape[1] if kwargs.get("b_mn") else b.shape[0]
+            return 2.0 * m * n * k
+        if name in ("attention_fwd", "attention_bwd"):
+            q, k = args[0], args[1]
+            bb, nq, h, d = q.shape
+            return (4.0 if name == "attention_fwd" else 8.0) * bb * h * nq * k.shape[1] * d
+        return 0.0
+
+    def wrap(name):
+        fn = getattr(_C, name)
+        originals[name] = fn
+
+        def timed(*args, **kwargs):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*args, **kwargs)
+            e.record()
+            records.append((name, flops_of(name, args, kwargs), s, e))
+            return r
+
+        setattr(_C, name, timed)
+
+    names = ["gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16",
+             "mask_to_index", "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize",
+             "gather_patches", "scatter_patches", "masked_mse_fwd", "sumsq", "adamw_flat"]
+    for n in names:
+        wrap(n)
+    try:
+        s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_all.record()
+        trainer.eager_step(batch_dev)
+        e_all.record()
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in originals.items():
+            setattr(_C, n, fn)
+    agg: dict[str, list[float]] = {}
+    for name, fl, s, e in records:
+        a = agg.setdefault(name, [0.0, 0.0, 0])
+        a[0] += s.elapsed_time(e)
+        a[1] += fl
+        a[2] += 1
+    total = s_all.elapsed_time(e_all)
+    own = sum(a[0] for a in agg.values())
+    return {"step_ms": total, "own_kernels_ms": own, "stem_and_other_ms": total - own,
+            "kernels": {k: {"ms": round(v[0], 3), "launches": v[2], "tflops": round(v[1] / v[0] / 1e9, 1) if v[0] > 0 and v[1] else None}
+                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}}
+
+
+# ------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="frame-sets per GPU per step (reference: batch_size_per_device 16)")
+    ap.add_argument("--size", default="base", choices=["base", "large"])
+    ap.add_argument("--lax", type=int, default=192, help="LAX edge: 192 (BASELINE.json wording) or 256 (reference default)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kw = model_kwargs(args.size, (192, 192, 16), (args.lax, args.lax))
+    work = train_gflop_per_sample(kw)
+    workload = (f"4-view cine frame-set: SAX 192x192x16 + 3 LAX {args.lax}x{args.lax}, ViT-{args.size[0].upper()} MAE, mask 0.75, "
+                f"enc/q/kv tokens {work['enc_tokens']}/{work['q_tokens']}/{work['kv_tokens']}")
+    config = {"workload": workload, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+              "optimizer": "AdamW lr 1e-3 betas (0.9, 0.95) wd 0.05, clip 5.0", "train_gflop_per_volume": round(work["train_gflop"], 1),
+              "cache": "per-step working set (activations > 5 GB) far exceeds the 126 MB L2; no flush needed",
+              "cine32_volumes": "divide value by 32 for 32-frame cine volumes/s"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_b = 2 if args.steps + args.warmup <= 30 else 1
+        cpu = cpu_reference_throughput(kw, sample_b, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "mae_pretrain_volumes_per_sec", "value": cpu["value"], "unit": "frame-set volumes/s",
+                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {**config, "batch_per_gpu": sample_b, "global_batch": sample_b, "parallelism": "cpu"},
+                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cpu["value"], "unit": "frame-set volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch.distributed as dist
+
+    from cinema_b200 import CineMA, _C
+    from cinema_b200.train import MAETrainer
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.lib()
+    torch.backends.cudnn.benchmark = True  # cinema/device.py:63
+    torch.manual_seed(0 + rank)            # cinema/mae/pretrain.py:309-310
+    model = CineMA(**kw).to(dev)
+    model.train()
+    trainer = MAETrainer(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05, clip_grad=5.0, enc_mask_ratio=0.75,
+                         use_cuda_graph=not args.no_graph)
+    host = synthetic_batch(kw, args.batch, seed=rank, pin=True)
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps: int) -> float:
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident() -> None:
+        trainer.step(resident)
+
+    def step_e2e() -> None:
+        loss = trainer.step(host)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host reads this step's loss
+
+    for _ in range(warmup):
+        step_e2e()
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(step_resident, args.steps)
+        ms_e2e = timed(step_e2e, args.steps)
+    final_loss = float(loss_host[0])
+    n_vol = args.batch * world * args.steps
+    value = n_vol / (ms / 1e3)
+    e2e_value = n_vol / (ms_e2e / 1e3)
+
+    peaks, peak_kind = measured_peaks()
+    prof = None
+    if not args.no_kernel_profile:
+        prof = instrumented_step(trainer, resident)
+    line = {
+        "metric": "mae_pretrain_volumes_per_sec", "value": round(value, 2), "unit": "frame-set volumes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+        "e2e": {"value": round(e2e_value, 2), "unit": "frame-set volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": trainer.launches_per_step * args.steps, "gpu_launches_per_step": trainer.launches_per_step,
+        "cuda_graph": trainer.use_graph, "final_loss": final_loss, "clocks": clocks.summary(),
+    }
+    sustained = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    step_tflops = value / world * work["train_gflop"] / 1e3
+    line["step_roofline"] = {"bound": "tensor", "achieved": round(step_tflops, 1), "peak": sustained, "unit": "TFLOP/s",
+                             "frac": round(step_tflops / sustained, 4), "note": f"whole step per GPU, algorithmic train FLOPs, {peak_kind} sustained peak"}
+    if prof is not None:
+        g = prof["kernels"].get("gemm")
+        if g and g["tflops"]:
+            line["roofline"] = {"bound": "tensor", "achieved": g["tflops"], "peak": sustained, "unit": "TFLOP/s",
+                                "frac": round(g["tflops"] / sustained, 4), "traffic": None,
+                                "kernel": "gemm_bf16_kernel (all GEMM launches of one step, CUDA events per launch)",
+                                "share_of_step": round(g["ms"] / prof["step_ms"], 3), "peak_kind": f"{peak_kind} sustained"}
+        line["kernel_profile"] = prof
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_throughput(kw, 2, 2, 1)
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

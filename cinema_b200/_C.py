@@ -55,6 +55,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
     "cb_colsum_seg_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cb_scale_cast_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_void_p]),
+    "cb_sumsq_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
+    "cb_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_float,
+                              c_float, c_float, c_void_p, c_float, c_float, c_void_p]),
     "cb_mae_loss_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cb_gather_patches": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p,
@@ -363,3 +366,22 @@ def masked_mse_fwd(image, patch, mask, slot, pred, norm_target: bool, eps: float
     _check(lib().cb_masked_mse_fwd(_ptr(image), b, c, len(spatial), _ints(spatial), _ints(patch), _ptr(mask),
                                    _ptr(slot), _ptr(pred), pred.shape[1], int(norm_target), float(eps), _ptr(acc),
                                    _ptr(diff), _stream()), "masked_mse_fwd")
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[0] += sum(x^2) over a flat fp32 buffer."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.float32
+    _check(lib().cb_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "sumsq")
+
+
+def adamw_flat(p, g, m, v, p16, hyper, beta1: float, beta2: float, eps: float, weight_decay: float, gnorm_sq,
+               max_norm: float, grad_scale: float) -> None:
+    """AdamW + clipping + bf16 shadow refresh on a flat fp32 segment; hyper = device [lr, 1-b1^t, 1-b2^t]."""
+    n = p.numel()
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    assert p16 is None or (p16.dtype == torch.bfloat16 and p16.numel() == n)
+    assert hyper.dtype == torch.float32 and hyper.numel() >= 3
+    _check(lib().cb_adamw_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), n, _ptr(hyper), float(beta1), float(beta2),
+                               float(eps), float(weight_decay), _ptr(gnorm_sq), float(max_norm), float(grad_scale),
+                               _stream()), "adamw_flat")

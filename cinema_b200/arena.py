@@ -44,17 +44,23 @@ class ParamArena:
         if any(p.dtype != torch.float32 for p in params):
             raise ValueError("cinema_b200 keeps fp32 master parameters (reference state-dict contract)")
 
+        names = {id(p): n for n, p in root.named_parameters()}
         order: list[list[nn.Parameter]] = []
         placed: set[int] = set()
         for g in groups:
             g = [p for p in g if id(p) in seen]
             if len(g) < 2 or any(id(p) in placed for p in g) or any(p.numel() % 8 for p in g[:-1]):
                 continue  # cannot be laid out back to back with 16-byte aligned members; callers re-check adjacency
+            if len({self.category(p, names[id(p)]) for p in g}) != 1:
+                continue
             order.append(g)
             placed.update(id(p) for p in g)
         for p in params:
             if id(p) not in placed:
                 order.append([p])
+        # optimiser regions: [weight-decayed | not decayed | frozen] so that AdamW is a few long flat launches
+        order.sort(key=lambda g: self.category(g[0], names[id(g[0])]))
+        self._names = names
 
         offsets: dict[int, int] = {}
         cur = 0
@@ -74,7 +80,10 @@ class ParamArena:
         self._w16: dict[int, torch.Tensor] = {}
         self._g32: dict[int, torch.Tensor] = {}
         self._off = offsets
-        self.shadow_valid = False
+        self.shadow_managed = False  # True while an optimiser kernel keeps flat16 in sync with flat32
+        self._group_starts = []
+        for g in order:
+            self._group_starts.append((offsets[id(g[0])], g))
         with torch.no_grad():
             for p in params:
                 off, n = offsets[id(p)], p.numel()
@@ -87,6 +96,27 @@ class ParamArena:
                     self._g32[id(p)].copy_(p.grad)
                     p.grad = self._g32[id(p)]
                 p._cb_arena = weakref.ref(self)  # type: ignore[attr-defined]
+
+    @staticmethod
+    def category(p: nn.Parameter, name: str) -> int:
+        """0: trainable with weight decay, 1: trainable without (1-D tensors and biases, the rule of timm's
+        ``param_groups_weight_decay`` used at cinema/mae/pretrain.py:365), 2: frozen."""
+        if not p.requires_grad:
+            return 2
+        return 1 if (p.ndim <= 1 or name.endswith(".bias")) else 0
+
+    def segments(self) -> list[tuple[int, int, int]]:
+        """Maximal runs (start, end, category) of the arena under the CURRENT requires_grad flags."""
+        runs: list[list[int]] = []
+        for start, g in self._group_starts:
+            cat = max(self.category(p, self._names[id(p)]) for p in g) if len(
+                {self.category(p, self._names[id(p)]) for p in g}) > 1 else self.category(g[0], self._names[id(g[0])])
+            if runs and runs[-1][2] == cat:
+                continue
+            if runs:
+                runs[-1][1] = start
+            runs.append([start, self.numel, cat])
+        return [(a, b, c) for a, b, c in runs]
 
     # ------------------------------------------------------------------ queries
     def owns(self, p: nn.Parameter) -> bool:
@@ -132,8 +162,9 @@ class ParamArena:
     # ------------------------------------------------------------------ per-step work
     def refresh_shadow(self) -> None:
         """fp32 master -> bf16 shadow: one HBM-bound kernel over the whole arena (6 B / parameter)."""
+        if self.shadow_managed:
+            return
         _C.cast_bf16(self.flat32, self.flat16)
-        self.shadow_valid = True
 
     def prepare_grads(self) -> None:
         """Make every trainable parameter's ``.grad`` the arena view (zero-filled when it was ``None``),

@@ -1,0 +1,174 @@
+"""Data-parallel MAE pre-training step on B200: the step recipe of the reference's
+``pretrain_one_epoch`` (cinema/mae/pretrain.py:242-272) with its runtime pieces re-designed:
+
+  reference                                         here
+  ------------------------------------------------  -------------------------------------------------
+  batch.to(device) per view                         pinned host buffers -> static device buffers (async)
+  autocast forward + autograd backward (~4k nodes)  one fused autograd node, replayed as a CUDA graph
+  DDP reducer, 25 MB fp32 buckets, every micro-step ONE NCCL all-reduce of the flat gradient arena
+  GradScaler.unscale_ + clip_grad_norm_ + AdamW     sum-of-squares kernel + one fused AdamW kernel per
+  (~10 passes over ~600 tensors)                    arena region (clip folded in, bf16 shadow refreshed)
+  metrics .item() x 14 (host syncs)                 loss copied to pinned memory, read one step later
+
+``cosine_lr`` restates ``adjust_learning_rate`` (cinema/optim.py:21-52).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from cinema_b200 import _C
+from cinema_b200.arena import ensure_arena
+
+
+def cosine_lr(step: float, warmup_steps: float, max_n_steps: float, lr: float, min_lr: float) -> float:
+    """Linear warm-up then half-cycle cosine decay (cinema/optim.py:21-52)."""
+    if step < warmup_steps:
+        return lr * step / warmup_steps
+    return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * (step - warmup_steps) / (max_n_steps - warmup_steps)))
+
+
+class FlatAdamW:
+    """AdamW over the flat arena with global-norm clipping (cinema/mae/pretrain.py:365-367, cinema/optim.py:204-212)."""
+
+    def __init__(self, arena, lr: float, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.05,
+                 clip_grad: float | None = 5.0) -> None:
+        self.arena = arena
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.clip_grad = clip_grad if clip_grad and clip_grad > 0 else 0.0
+        dev = arena.device
+        self.m = torch.zeros_like(arena.flat32)
+        self.v = torch.zeros_like(arena.flat32)
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(4, dtype=torch.float32)
+        if dev.type == "cuda":
+            self._hyper_host = self._hyper_host.pin_memory()
+        self.t = 0
+        self.segments = [s for s in arena.segments() if s[2] != 2]
+
+    def set_step_scalars(self) -> None:
+        """Host -> device copy of {lr, 1 - beta1^t, 1 - beta2^t} for the NEXT ``apply`` (outside any CUDA graph)."""
+        self.t += 1
+        self._hyper_host[0] = self.lr
+        self._hyper_host[1] = 1.0 - self.betas[0] ** self.t
+        self._hyper_host[2] = 1.0 - self.betas[1] ** self.t
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def apply(self, grad_scale: float = 1.0) -> None:
+        """Norm + clip + AdamW + bf16 shadow refresh; graph-capturable (no host-dependent values)."""
+        a = self.arena
+        self.gnorm_sq.zero_()
+        for s, e, _ in self.segments:
+            _C.sumsq(a.gflat[s:e], self.gnorm_sq)
+        for s, e, cat in self.segments:
+            _C.adamw_flat(a.flat32[s:e], a.gflat[s:e], self.m[s:e], self.v[s:e], a.flat16[s:e], self.hyper, self.betas[0],
+                          self.betas[1], self.eps, self.weight_decay if cat == 0 else 0.0, self.gnorm_sq, self.clip_grad,
+                          grad_scale)
+
+    def grad_norm(self, grad_scale: float = 1.0) -> torch.Tensor:
+        return self.gnorm_sq.sqrt() * grad_scale
+
+
+class MAETrainer:
+    """One object = one rank.  ``step(batch)`` runs H2D -> forward -> backward -> all-reduce -> clip -> AdamW."""
+
+    def __init__(self, model: nn.Module, *, lr: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.05,
+                 clip_grad: float | None = 5.0, enc_mask_ratio: float = 0.75, use_cuda_graph: bool = True,
+                 process_group=None, graph_warmup: int = 3) -> None:
+        self.model = model
+        self.ratio = enc_mask_ratio
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.arena = ensure_arena(model)
+        if self.world > 1:  # rank 0's initial weights everywhere (cinema/mae/pretrain.py:345-361)
+            dist.broadcast(self.arena.flat32, src=0, group=self.pg)
+        self.arena.shadow_managed = False
+        self.arena.refresh_shadow()
+        self.arena.shadow_managed = True
+        model.register_load_state_dict_post_hook(lambda *_: self.sync_shadow())
+        self.arena.gflat.zero_()
+        self.arena.prepare_grads()
+        self.opt = FlatAdamW(self.arena, lr, betas, 1e-8, weight_decay, clip_grad)
+        self.use_graph = use_cuda_graph and self.arena.device.type == "cuda"
+        self.graph_warmup = graph_warmup
+        self._n_calls = 0
+        self._inputs: dict[str, torch.Tensor] | None = None
+        self._g_fb = self._g_opt = None
+        self._loss = None
+        self._loss_host = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ pieces
+    def sync_shadow(self) -> None:
+        self.arena.shadow_managed = False
+        self.arena.refresh_shadow()
+        self.arena.shadow_managed = True
+
+    def set_lr(self, lr: float) -> None:
+        self.opt.lr = lr
+
+    def _stage(self, batch: dict[str, torch.Tensor]) -> None:
+        dev = self.arena.device
+        if self._inputs is None:
+            self._inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+        for k, v in batch.items():
+            self._inputs[k].copy_(v, non_blocking=True)
+
+    def _fwd_bwd(self) -> None:
+        self.arena.gflat.zero_()
+        loss, _, _, _ = self.model(self._inputs, self.ratio)
+        loss.backward()
+        self._loss = loss.detach()
+
+    def _reduce(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.arena.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _opt_apply(self) -> None:
+        self.opt.apply(grad_scale=1.0 / self.world)
+
+    # ------------------------------------------------------------------ the step
+    def step(self, batch: dict[str, torch.Tensor]) -> torch.Tensor:
+        """batch: {view: (B, C, *spatial)} host (pinned) or device tensors.  Returns the loss as a 0-d DEVICE tensor
+        (valid until the next call); nothing here synchronises with the host."""
+        self._stage(batch)
+        self.opt.set_step_scalars()
+        if not self.use_graph or self._n_calls < self.graph_warmup:
+            n0 = _C.launches
+            self._fwd_bwd()
+            self._reduce()
+            self._opt_apply()
+            self.launches_per_step = _C.launches - n0
+        else:
+            if self._g_fb is None:
+                self._capture()
+            self._g_fb.replay()
+            self._reduce()
+            self._g_opt.replay()
+        self._n_calls += 1
+        return self._loss
+
+    def eager_step(self, batch: dict[str, torch.Tensor]) -> torch.Tensor:
+        """The same step without CUDA-graph replay (used for per-kernel instrumentation)."""
+        self._stage(batch)
+        self.opt.set_step_scalars()
+        self._fwd_bwd()
+        self._reduce()
+        self._opt_apply()
+        return self._loss
+
+    def _capture(self) -> None:
+        torch.cuda.synchronize()
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._fwd_bwd()
+        self._g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
+            self._opt_apply()
+        # the capture pass recorded, it did not run: play the step that was asked for
+        # (callers replay right after)

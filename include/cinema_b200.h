@@ -166,6 +166,18 @@ int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, const int* spa
 int cb_mae_loss_finalize(const float* acc, int n_views, const float* sq_count, const float* patch_count, float* out,
                          float* scales, void* stream);
 
+/* ---- optimiser step over the flat arena ------------------------------------------------- *
+ * out[0] += sum x^2 (global gradient norm, torch.nn.utils.clip_grad_norm_ at cinema/optim.py:206). */
+int cb_sumsq_f32(const float* x, long long n, float* out, void* stream);
+/* AdamW (torch.optim.AdamW semantics, decoupled weight decay) on a flat segment, fused with gradient
+ * clipping and the bf16 shadow refresh.  hyper (DEVICE) = {lr, 1 - beta1^t, 1 - beta2^t}.  gnorm_sq
+ * (DEVICE, may be NULL) = sum of squared gradients of the whole model BEFORE grad_scale; the applied
+ * gradient is g * grad_scale * min(1, max_norm / (sqrt(gnorm_sq) * grad_scale + 1e-6)); a non-finite
+ * norm skips the step (GradScaler semantics, cinema/optim.py:204-212).  p16 may be NULL. */
+int cb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, long long n, const float* hyper, float beta1,
+                  float beta2, float eps, float weight_decay, const float* gnorm_sq, float max_norm, float grad_scale,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,6 +286,28 @@ def rope_apply(x, cos, sin, transpose=False):
     return torch.cat([(head * c + rot * s).to(x.dtype), x[..., ro:]], -1)
 
 
+def sumsq(x, out):
+    out[0] += (x.double() ** 2).sum().float()
+
+
+def adamw_flat(p, g, m, v, p16, hyper, beta1, beta2, eps, weight_decay, gnorm_sq, max_norm, grad_scale):
+    lr, bc1, bc2 = (float(hyper[i]) for i in range(3))
+    gs = grad_scale
+    if gnorm_sq is not None:
+        norm = float(gnorm_sq.reshape(-1)[0]) ** 0.5 * grad_scale
+        if not math.isfinite(norm):
+            return
+        if max_norm > 0:
+            gs *= min(1.0, max_norm / (norm + 1e-6))
+    gg = g * gs
+    m.mul_(beta1).add_(gg, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    p.mul_(1 - lr * weight_decay).addcdiv_(m, denom, value=-lr / bc1)
+    if p16 is not None:
+        p16.copy_(p.to(BF16))
+
+
 def device_info():
     return 148, 10, 0
 
@@ -293,5 +315,5 @@ def device_info():
 ALL = [
     "gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16", "mask_to_index",
     "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize", "patchify",
-    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply",
+    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply", "sumsq", "adamw_flat",
 ]

@@ -154,6 +154,18 @@ CASES = {
         ),
         batch=3, ratio=0.5,
     ),
+    # same two switches at the head dims the tcgen05 attention kernels are built for (64 encoder / 32 decoder)
+    "mae_hd_selfattn_normtarget": dict(
+        kw=dict(
+            image_size_dict={"sax": (32, 32, 2), "lax_2c": (48, 48)}, in_chans_dict={"sax": 1, "lax_2c": 1},
+            enc_patch_size_dict={"sax": (4, 4, 1), "lax_2c": (4, 4)},
+            enc_scale_factor_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)},
+            enc_conv_chans=[8, 16], enc_conv_n_blocks=1,
+            enc_embed_dim=64, enc_depth=2, enc_n_heads=1, dec_embed_dim=64, dec_depth=2, dec_n_heads=2,
+            cross_attn=False, norm_target=True,
+        ),
+        batch=3, ratio=0.5,
+    ),
 }
 
 GRAD_KEYS = [
@@ -265,9 +277,12 @@ def make_op_vectors() -> None:
 
 
 def main() -> None:
+    only = sys.argv[1:]
     for name, spec in CASES.items():
-        make_mae_case(name, spec)
-    make_op_vectors()
+        if not only or name in only:
+            make_mae_case(name, spec)
+    if not only or "ops" in only:
+        make_op_vectors()
 
 
 if __name__ == "__main__":

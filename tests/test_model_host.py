@@ -23,7 +23,7 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-CASES = ["mae_tiny_sax", "mae_small_4view", "mae_tiny_selfattn_normtarget"]
+CASES = ["mae_tiny_sax", "mae_small_4view", "mae_tiny_selfattn_normtarget", "mae_hd_selfattn_normtarget"]
 
 
 @pytest.mark.parametrize("case", CASES)
