@@ -41,10 +41,15 @@ _SIGNATURES = {
                          + [c_void_p, c_longlong, c_longlong, c_longlong] * 3
                          + [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "cb_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_longlong,
-                                 c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_void_p]),
     "cb_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong,
-                                 c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_expand_token_index": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_dwconv_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "cb_dwconv_tokens_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cb_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "cb_mask_to_index": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_gather_rows": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p, c_longlong, c_longlong,
@@ -196,16 +201,17 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale: float) 
                                   _ptr(dq_acc), b, h, nq, nk, d, float(scale), _stream()), "attention_bwd")
 
 
-def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None) -> None:
+def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None, act: bool = False) -> None:
     m, d = x.shape
     assert x.dtype == torch.float32 and gamma.dtype == torch.float32 and beta.dtype == torch.float32
     _check(lib().cb_layernorm_fwd(_ptr(x), _row_major_2d(x, "x"), _ptr(gamma), _ptr(beta), m, d, float(eps),
                                   _ptr(y16), _row_major_2d(y16, "y16") if y16 is not None else 0,
                                   _ptr(y32), _row_major_2d(y32, "y32") if y32 is not None else 0,
-                                  _ptr(mean), _ptr(rstd), _stream()), "layernorm_fwd")
+                                  _ptr(mean), _ptr(rstd), int(act), _stream()), "layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None) -> None:
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None,
+                  beta_act=None) -> None:
     m, d = x.shape
     dt = DT_BF16 if dy.dtype == torch.bfloat16 else DT_F32
     assert dy.dtype in (torch.bfloat16, torch.float32) and x.dtype == torch.float32
@@ -214,7 +220,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dga
                                   _row_major_2d(dres, "dres") if dres is not None else 0, m, d,
                                   _ptr(dx32), _row_major_2d(dx32, "dx32") if dx32 is not None else 0,
                                   _ptr(dx16), _row_major_2d(dx16, "dx16") if dx16 is not None else 0,
-                                  _ptr(dgamma), _ptr(dbeta), _stream()), "layernorm_bwd")
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(beta_act), _stream()), "layernorm_bwd")
 
 
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -385,3 +391,38 @@ def adamw_flat(p, g, m, v, p16, hyper, beta1: float, beta2: float, eps: float, w
     _check(lib().cb_adamw_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), n, _ptr(hyper), float(beta1), float(beta2),
                                float(eps), float(weight_decay), _ptr(gnorm_sq), float(max_norm), float(grad_scale),
                                _stream()), "adamw_flat")
+
+
+def expand_token_index(keep: torch.Tensor, grid_tok, f) -> torch.Tensor:
+    """(B, nk) visible token ids -> (B, nk * prod(f)) position ids in the level grid grid_tok * f."""
+    assert keep.dtype == torch.int32 and keep.is_contiguous()
+    b, nk = keep.shape
+    p = 1
+    for x in f:
+        p *= int(x)
+    out = torch.empty((b, nk * p), dtype=torch.int32, device=keep.device)
+    _check(lib().cb_expand_token_index(_ptr(keep), b, nk, len(f), _ints(grid_tok), _ints(f), _ptr(out), _stream()),
+           "expand_token_index")
+    return out
+
+
+def dwconv_tokens(x, out, w, bias, mask, slot, keep, grid_tok, f, transpose: bool = False) -> None:
+    """Depth-wise 5^n conv over token-major channel-last rows x (B*nk*P, C) bf16 -> out (same shape)."""
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous() and x.shape == out.shape
+    assert mask.dtype == torch.bool and mask.is_contiguous() and slot.dtype == torch.int32 and keep.dtype == torch.int32
+    b, nk = keep.shape
+    c = x.shape[-1]
+    assert w.shape[0] == c and (bias is None or (bias.dtype == torch.float32 and bias.numel() == c))
+    _check(lib().cb_dwconv_tokens(_ptr(x), _ptr(out), _ptr(w), _ptr(bias), _ptr(mask), _ptr(slot), _ptr(keep), b, nk, c,
+                                  len(f), _ints(grid_tok), _ints(f), int(transpose), _stream()), "dwconv_tokens")
+
+
+def dwconv_tokens_wgrad(x, dy, dw, db, mask, slot, keep, grid_tok, f) -> None:
+    """dw (C, 1, 5, 5[, 5]) fp32 += correlation(dy, x); db (C) fp32 += colsum(dy)."""
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.shape == dy.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dw.dtype == torch.float32 and dw.is_contiguous()
+    b, nk = keep.shape
+    c = x.shape[-1]
+    _check(lib().cb_dwconv_tokens_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(mask), _ptr(slot), _ptr(keep), b, nk, c,
+                                        len(f), _ints(grid_tok), _ints(f), _stream()), "dwconv_tokens_wgrad")

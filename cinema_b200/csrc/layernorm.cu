@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      int M, int D, float eps, bf16* __restrict__ y16, long long ldy16,
                                                      float* __restrict__ y32, long long ldy32, float* __restrict__ mean_o,
-                                                     float* __restrict__ rstd_o) {
+                                                     float* __restrict__ rstd_o, int act) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = D >> 2;
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (act) o.x = gelu_f(o.x), o.y = gelu_f(o.y), o.z = gelu_f(o.z), o.w = gelu_f(o.w);
         if (y32) reinterpret_cast<float4*>(y32 + row * ldy32)[c] = o;
         if (y16) reinterpret_cast<uint2*>(y16 + row * ldy16)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
                                                      long long lddres, int M, int D, float* __restrict__ dx32,
                                                      long long lddx32, bf16* __restrict__ dx16, long long lddx16,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     const float* __restrict__ beta_act) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = D >> 2;
@@ -100,6 +102,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
         const float4 xv = __ldg(xr + c);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        if (beta_act != nullptr) {  // the forward applied GELU to the LN output: dy <- dy * GELU'(xhat * gamma + beta)
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(beta_act) + c);
+          d.x *= gelu_grad_f(fmaf(xh[i].x, g.x, bb.x)), d.y *= gelu_grad_f(fmaf(xh[i].y, g.y, bb.y));
+          d.z *= gelu_grad_f(fmaf(xh[i].z, g.z, bb.z)), d.w *= gelu_grad_f(fmaf(xh[i].w, g.w, bb.w));
+        }
         dyg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
         s1 += dyg[i].x + dyg[i].y + dyg[i].z + dyg[i].w;
         s2 += dyg[i].x * xh[i].x + dyg[i].y * xh[i].y + dyg[i].z * xh[i].z + dyg[i].w * xh[i].w;
@@ -172,7 +179,7 @@ inline int pick_nv(int D) {
 
 extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, int M, int D,
                                 float eps, void* y16, long long ldy16, float* y32, long long ldy32, float* mean,
-                                float* rstd, void* stream) {
+                                float* rstd, int act, void* stream) {
   if (M <= 0) return 0;
   CB_CHECK_ARG(D > 0 && D % 4 == 0 && D <= 2048, "layernorm: D=%d must be a multiple of 4 and <= 2048", D);
   CB_CHECK_ARG(ldx % 4 == 0 && (y16 == nullptr || ldy16 % 4 == 0) && (y32 == nullptr || ldy32 % 4 == 0),
@@ -181,13 +188,13 @@ extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamm
   const int blocks = (int)min((long long)(M + 7) / 8, (long long)cb_sm_count() * 8);
   cudaStream_t s = (cudaStream_t)stream;
   switch (nv) {
-    LN_DISPATCH(1, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(2, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(4, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(6, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(8, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(12, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
-    LN_DISPATCH(16, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd)))
+    LN_DISPATCH(1, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(2, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(4, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(6, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(8, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(12, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(16, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
     default: CB_CHECK_ARG(false, "layernorm: unsupported D=%d", D);
   }
   CB_LAUNCH_CHECK();
@@ -197,7 +204,7 @@ extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamm
 extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, const float* x, long long ldx,
                                 const float* mean, const float* rstd, const float* gamma, const float* dres,
                                 long long lddres, int M, int D, float* dx32, long long lddx32, void* dx16,
-                                long long lddx16, float* dgamma, float* dbeta, void* stream) {
+                                long long lddx16, float* dgamma, float* dbeta, const float* beta_act, void* stream) {
   if (M <= 0) return 0;
   CB_CHECK_ARG(D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: D=%d must be a multiple of 4 and <= 2048", D);
   CB_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0, "layernorm_bwd: row pitches must be multiples of 4 elements");
@@ -208,7 +215,7 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
   cudaStream_t s = (cudaStream_t)stream;
 #define LN_BWD_CALL(BF)                                                                                              \
   ln_bwd_kernel<NV, BF><<<blocks, 256, smem, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, D, dx32, lddx32, \
-                                                  (bf16*)dx16, lddx16, dgamma, dbeta)
+                                                  (bf16*)dx16, lddx16, dgamma, dbeta, beta_act)
   const bool bf = dy_dtype == CB_DT_BF16;
   switch (nv) {
     LN_DISPATCH(1, if (bf) LN_BWD_CALL(true); else LN_BWD_CALL(false))

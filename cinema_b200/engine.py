@@ -136,7 +136,7 @@ def normw(arena: ParamArena, ln: nn.LayerNorm, train: bool) -> NormW:
 
 
 def ln_fwd(x32: torch.Tensor, w: NormW, *, want16: bool = True, want32: bool = False, stats: bool = True,
-           y16: torch.Tensor | None = None):
+           y16: torch.Tensor | None = None, act: bool = False):
     m, d = x32.shape
     dev = x32.device
     if want16 and y16 is None:
@@ -144,18 +144,20 @@ def ln_fwd(x32: torch.Tensor, w: NormW, *, want16: bool = True, want32: bool = F
     y32 = torch.empty((m, d), dtype=F32, device=dev) if want32 else None
     mean = torch.empty(m, dtype=F32, device=dev) if stats else None
     rstd = torch.empty(m, dtype=F32, device=dev) if stats else None
-    _C.layernorm_fwd(x32, w.gamma, w.beta, w.eps, y16=y16, y32=y32, mean=mean, rstd=rstd)
+    _C.layernorm_fwd(x32, w.gamma, w.beta, w.eps, y16=y16, y32=y32, mean=mean, rstd=rstd, act=act)
     return y16, y32, mean, rstd
 
 
 def ln_bwd(dy: torch.Tensor, x32: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, w: NormW, *,
-           dres: torch.Tensor | None = None, want16: bool = True, dx32: torch.Tensor | None = None):
+           dres: torch.Tensor | None = None, want16: bool = True, dx32: torch.Tensor | None = None,
+           beta_act: torch.Tensor | None = None):
     """dx = LN'(dy) + dres -> (dx32, dx16).  ``dx32`` may alias ``dres`` (row-local read-then-write)."""
     m, d = x32.shape
     if dx32 is None:
         dx32 = torch.empty((m, d), dtype=F32, device=x32.device)
     dx16 = torch.empty((m, d), dtype=BF16, device=x32.device) if want16 else None
-    _C.layernorm_bwd(dy, x32, mean, rstd, w.gamma, dres=dres, dx32=dx32, dx16=dx16, dgamma=w.gg, dbeta=w.gb)
+    _C.layernorm_bwd(dy, x32, mean, rstd, w.gamma, dres=dres, dx32=dx32, dx16=dx16, dgamma=w.gg, dbeta=w.gb,
+                     beta_act=beta_act)
     return dx32, dx16
 
 

@@ -25,7 +25,7 @@ import math
 import torch
 from torch import nn
 
-from cinema_b200 import _C, engine
+from cinema_b200 import _C, engine, stem
 from cinema_b200.arena import ensure_arena
 from cinema_b200.conv import Linear
 from cinema_b200.convvit import DownsampleEncoder, MultiScaleFusion
@@ -117,6 +117,17 @@ def _rows(t: torch.Tensor, start: int, count: int) -> torch.Tensor:
     return t[start:start + count]
 
 
+def model_grid(model, view, source_levels):
+    """ViT token grid of this call for ``view`` (stored on the source list by the callers)."""
+    return source_levels.token_grid
+
+
+class _Sources(list):
+    """Per-view list of (src, grid, idx) gather sources plus the ViT token grid they describe."""
+
+    token_grid: tuple[int, ...] = ()
+
+
 class _Encoded:
     """Saved state of the encoder half (embedding -> ViT encoder -> fusion), shared by MAE and feature paths."""
 
@@ -125,12 +136,14 @@ def _lin_of(arena, mod, train):
     return engine.linw(arena, mod.weight, mod.bias, train)
 
 
-def _encode(model, arena, views, feats, skips, keep, n_keeps, grids, b, train, want_fused32):
+def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32):
     """Visible-token embedding, ViT encoder and multi-scale fusion.
 
-    feats[v]: last stem feature map (or the image when there is no stem); skips[v]: per-level maps;
-    keep[v]: (B, n_keep) int32 ascending token ids.  Returns (F16, fused32 | None, state)."""
-    dev = feats[0].device
+    sources[v]: per stem level a triple (src, grid, idx) such that ``gather_patches(src, grid, patch, idx, ...)`` yields
+    one row per visible token -- either a dense (B, C, *spatial) map with the token grid and ``keep`` ids, or the
+    token-major output of the native stem viewed as (T, C, *f) with a unit grid; the last entry feeds the patch
+    embedding (for a model without stem it is the image).  Returns (F16, fused32 | None, state)."""
+    dev = keep[0].device
     d = model.encoder.cls_token.shape[-1]
     n = 1 + sum(n_keeps)
     st = _Encoded()
@@ -145,15 +158,15 @@ def _encode(model, arena, views, feats, skips, keep, n_keeps, grids, b, train, w
         nk = n_keeps[i]
         offs.append(off)
         ps = tuple(down.patch_sizes[-1])
-        src = feats[i]
+        src, sgrid, sidx = sources[i][-1]
         e_in = src.shape[1] * math.prod(ps)
         p16 = torch.empty((b * nk, e_in), dtype=BF16, device=dev)
-        _C.gather_patches(src, grids[i], ps, keep[i], True, p16)
+        _C.gather_patches(src, sgrid, ps, sidx, True, p16)
         w_pe = _lin_of(arena, down.patch_embed.proj, train)
         w_li = _lin_of(arena, down.linear, train)
         t1 = engine.linear_fwd(p16, w_pe)
         t2 = engine.linear_fwd(t1, w_li, out_dtype=F32)
-        pos = down.interpolate_pos_encoding(grids[i]).data.reshape(-1, d).contiguous()
+        pos = down.interpolate_pos_encoding(model_grid(model, v, sources[i])).data.reshape(-1, d).contiguous()
         _C.embed_rows(t2.view(b, nk, d), 0, None, pos, keep[i], b, nk, out=x0, out_off=off)
         st.embed.append((p16, t1, w_pe, w_li, ps))
         off += nk
@@ -189,9 +202,9 @@ def _encode(model, arena, views, feats, skips, keep, n_keeps, grids, b, train, w
         lv = []
         for lvl, conv in enumerate(fus.down_convs):
             k = tuple(conv.kernel_size)
-            skip = skips[i][lvl]
+            skip, sgrid, sidx = sources[i][lvl]
             pf = torch.empty((b * nk, skip.shape[1] * math.prod(k)), dtype=BF16, device=dev)
-            _C.gather_patches(skip, grids[i], k, keep[i], False, pf)
+            _C.gather_patches(skip, sgrid, k, sidx, False, pf)
             wc = _lin_of(arena, conv, train)
             cur_v = engine.linear_fwd(pf, wc, out_dtype=F32, residual=cur_v)
             lv.append((pf, wc, k))
@@ -206,13 +219,14 @@ def _encode(model, arena, views, feats, skips, keep, n_keeps, grids, b, train, w
     return f16, fused32, st
 
 
-def _encode_bwd(model, arena, views, st, d_f32, keep, n_keeps, grids, b, skips, skip_needs_grad):
-    """Backward of :func:`_encode` given d F (fp32, (B + B * sum n_keep, D)).  Returns per-view lists of skip gradients."""
+def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
+    """Backward of :func:`_encode` given d F (fp32, (B + B * sum n_keep, D)).  targets[v][lvl] = (dst, grid, idx) names the
+    pre-zeroed gradient buffer of source level lvl (same addressing as the source) or is None when no gradient is needed;
+    contributions are accumulated into it."""
     dev = d_f32.device
     n, d = st.n, st.d
     denc = torch.empty((b, n, d), dtype=F32, device=dev)
     _C.scatter_rows(d_f32[:b].view(b, 1, d), engine.arange_idx(b, 0, 1, dev), denc)
-    dskips = [[None] * len(skips[i]) for i in range(len(views))]
     for i, _ in enumerate(views):
         nk = n_keeps[i]
         lv, nw, cur_v, mean, rstd = st.fusion[i]
@@ -220,12 +234,10 @@ def _encode_bwd(model, arena, views, st, d_f32, keep, n_keeps, grids, b, skips, 
         dcur32, dcur16 = engine.ln_bwd(dyv, cur_v, mean, rstd, nw)
         _C.scatter_rows(dcur32.view(b, nk, d), engine.arange_idx(b, st.offs[i], nk, dev), denc)
         for lvl, (pf, wc, k) in enumerate(lv):
-            need = skip_needs_grad[i][lvl]
-            dpf = engine.linear_bwd(dcur16, pf, wc, need_dx=need)
-            if need:
-                g = torch.zeros_like(skips[i][lvl])
-                _C.scatter_patches(dpf, g, grids[i], k, keep[i], False, accumulate=True)
-                dskips[i][lvl] = g
+            tgt = targets[i][lvl]
+            dpf = engine.linear_bwd(dcur16, pf, wc, need_dx=tgt is not None)
+            if tgt is not None:
+                _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
     dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm)
     for j in range(len(st.enc_w) - 1, -1, -1):
         dx32, dx16 = engine.block_bwd(dx32, dx16, st.enc_w[j], b, st.enc_saved[j], None, None)
@@ -240,14 +252,80 @@ def _encode_bwd(model, arena, views, st, d_f32, keep, n_keeps, grids, b, skips, 
         dt2 = torch.empty((b, nk, d), dtype=BF16, device=dev)
         _C.embed_rows(dx0, st.offs[i], None, None, None, b, nk, out16=dt2)
         dt1 = engine.linear_bwd(dt2.view(b * nk, d), t1, w_li)
-        has_stem = len(skips[i]) > 0
-        need = has_stem and skip_needs_grad[i][-1]
-        dp = engine.linear_bwd(dt1, p16, w_pe, need_dx=need)
-        if need:
-            if dskips[i][-1] is None:
-                dskips[i][-1] = torch.zeros_like(skips[i][-1])
-            _C.scatter_patches(dp, dskips[i][-1], grids[i], ps, keep[i], True, accumulate=True)
-    return dskips
+        tgt = targets[i][-1] if targets[i] else None
+        dp = engine.linear_bwd(dt1, p16, w_pe, need_dx=tgt is not None)
+        if tgt is not None:
+            _C.scatter_patches(dp, tgt[0], tgt[1], ps, tgt[2], True, accumulate=True)
+
+
+
+def _needs(flags, counts):
+    out, pos = [], 0
+    for c in counts:
+        out.append([bool(f) for f in flags[pos:pos + c]])
+        pos += c
+    return out
+
+
+def _build_sources(model, arena, views, imgs32, skips, keep, masks, slot, grids, n_keeps, b, train):
+    """Gather sources of every view (see :func:`_encode`): the native visible-only stem when the view's stem is the
+    reference default (layer norm), else the dense feature maps computed by the caller (cuDNN path)."""
+    sources, stems = [], []
+    for i, v in enumerate(views):
+        down = model.enc_down_dict[v]
+        src = _Sources()
+        src.token_grid = grids[i]
+        if len(down.conv_blocks) == 0:
+            src.append((imgs32[i], grids[i], keep[i]))
+            stems.append(None)
+        elif skips[i]:
+            for sk in skips[i]:
+                src.append((sk, grids[i], keep[i]))
+            stems.append(None)
+        else:
+            levels = stem.stem_weights(arena, down, train)
+            geo = stem.Geometry(keep[i], masks[i].contiguous(), slot[i], grids[i], b, n_keeps[i])
+            outs, saved = stem.stem_fwd(levels, imgs32[i], geo, train)
+            t = b * n_keeps[i]
+            unit = (1,) * len(grids[i])
+            for lw, x in zip(levels, outs):
+                src.append((stem.level_view(x, t, lw.f), unit, None))
+            stems.append((levels, geo, saved))
+        sources.append(src)
+    return sources, stems
+
+
+def _build_targets(views, sources, stems, skips, needs):
+    """Gradient buffers matching the gather sources: fp32 token-major buffers for the native stem (always needed: the
+    stem parameters are upstream), zero-filled dense maps for cuDNN skips that require grad."""
+    targets, dskips = [], []
+    for i, _ in enumerate(views):
+        per_view, grads = [], []
+        if stems[i] is not None:
+            levels, geo, _ = stems[i]
+            t = geo.b * geo.nk
+            unit = (1,) * len(geo.grid_tok)
+            for lw, (src, _, _) in zip(levels, sources[i]):
+                buf = torch.zeros((t * math.prod(lw.f), lw.chans), dtype=F32, device=src.device)
+                per_view.append((stem.level_view(buf, t, lw.f), unit, None, buf))
+        elif skips[i]:
+            for lvl, sk in enumerate(skips[i]):
+                if needs[i][lvl]:
+                    g = torch.zeros_like(sk)
+                    grads.append(g)
+                    per_view.append((g, sources[i][lvl][1], sources[i][lvl][2]))
+                else:
+                    grads.append(None)
+                    per_view.append(None)
+        else:
+            per_view.append(None)  # the image needs no gradient
+        targets.append(per_view)
+        dskips.append(grads)
+    return targets, dskips
+
+
+def _native_grad_buffers(per_view_targets):
+    return [(t[3],) for t in per_view_targets]
 
 
 class _MAEFn(torch.autograd.Function):
@@ -259,12 +337,14 @@ class _MAEFn(torch.autograd.Function):
         if train:
             arena.prepare_grads()
         nv = len(views)
-        n_lvl = len(skips_flat) // nv
-        skips = [list(skips_flat[i * n_lvl:(i + 1) * n_lvl]) for i in range(nv)]
+        counts = model._dense_levels  # per view: number of dense (cuDNN) skip maps passed in, 0 for the native stem
+        skips, pos = [], 0
+        for c in counts:
+            skips.append(list(skips_flat[pos:pos + c]))
+            pos += c
         b = images[0].shape[0]
         dev = images[0].device
         imgs32 = [im.detach().to(F32).contiguous() for im in images]
-        feats = [skips[i][-1].detach() if n_lvl else imgs32[i] for i in range(nv)]
         skips = [[s.detach() for s in sk] for sk in skips]
         grids, keep, drop, slot, n_masks = [], [], [], [], []
         for i, v in enumerate(views):
@@ -275,7 +355,8 @@ class _MAEFn(torch.autograd.Function):
             keep.append(kd[0]), drop.append(kd[1]), slot.append(kd[2])
             n_masks.append(math.prod(grid) - n_keeps[i])
 
-        f16, _, st = _encode(model, arena, views, feats, skips, keep, n_keeps, grids, b, train, False)
+        sources, stems = _build_sources(model, arena, views, imgs32, skips, keep, masks, slot, grids, n_keeps, b, train)
+        f16, _, st = _encode(model, arena, views, sources, keep, n_keeps, b, train, False)
         d = st.d
         dd = model.dec_linear.weight.shape[0]
         w_dl = _lin_of(arena, model.dec_linear, train)
@@ -356,12 +437,12 @@ class _MAEFn(torch.autograd.Function):
 
         if train:
             ctx.state = dict(model=model, arena=arena, views=views, st=st, f16=f16, w_dl=w_dl, keep=keep, n_keeps=n_keeps,
-                             n_masks=n_masks, grids=grids, b=b, skips=skips, cross=cross, nq=nq, nk_tot=nk_tot,
+                             n_masks=n_masks, grids=grids, b=b, skips=skips, stems=stems, sources=sources, cross=cross,
+                             nq=nq, nk_tot=nk_tot,
                              xk16=xk16, kv_all=kv_all, kv_w=kv_w, kvs=kvs, dec_w=dec_w, dec_saved=dec_saved,
                              dec_norm=dec_norm, dec_last=cur, dmean=dmean, drstd=drstd, diffs=diffs, heads=heads,
                              dvs=dvs, scales=scales, koffs=koffs, qoffs=qoffs, dd=dd, d=d,
-                             needs=[[bool(ctx.needs_input_grad[6 + i * n_lvl + l]) for l in range(n_lvl)]
-                                    for i in range(nv)])
+                             needs=_needs(ctx.needs_input_grad[6:], counts))
         ctx.mark_non_differentiable(out, *preds)
         return (out[0], out, *preds)
 
@@ -431,7 +512,12 @@ class _MAEFn(torch.autograd.Function):
             if mt.requires_grad and nm > 0:
                 _C.colsum_seg(dxq, s["qoffs"][i], nm, arena.grad_view(mt).view(-1))
         d_f32 = engine.linear_bwd(dy16, s["f16"], s["w_dl"], dx_dtype=F32)
-        dskips = _encode_bwd(model, arena, views, st, d_f32, keep, n_keeps, s["grids"], b, s["skips"], s["needs"])
+        targets, dskips = _build_targets(views, s["sources"], s["stems"], s["skips"], s["needs"])
+        _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets)
+        for i, stem_state in enumerate(s["stems"]):
+            if stem_state is not None:
+                levels, geo, saved = stem_state
+                stem.stem_bwd(levels, geo, saved, [t[0] for t in _native_grad_buffers(targets[i])])
         flat = [g for per_view in dskips for g in per_view]
         return (None, None, None, None, None, None, *flat)
 
@@ -448,6 +534,8 @@ class CineMA(nn.Module):
                  rotary=False, act_layer=nn.GELU, mlp_layer=Mlp, drop_path=0.0, norm="layer") -> None:
         super().__init__()
         self.grad_ckpt = False
+        self.native_stem = True  # False: run the conv stem densely through cuDNN (reference evaluation order)
+        self._dense_levels: list[int] = []
         self.norm_target = norm_target
         self.views = list(image_size_dict.keys())
         self.enc_down_dict = nn.ModuleDict({
@@ -515,11 +603,19 @@ class CineMA(nn.Module):
         return views
 
     def _stem(self, views, image_dict, masks):
-        """Conv stem per view (bf16 autocast, cuDNN).  -> per-view lists of feature maps."""
+        """Dense (cuDNN, bf16 autocast) stem for the views whose stem the native visible-only path does not cover
+        (non-default ``norm``); an empty list for the others.  -> per-view lists of feature maps."""
         first = image_dict[views[0]]
+        out = []
         with torch.autocast(device_type="cuda", dtype=BF16, enabled=first.is_cuda):
-            return [self.enc_down_dict[v].conv_stem(image_dict[v], None if masks is None else masks[i])
-                    for i, v in enumerate(views)]
+            for i, v in enumerate(views):
+                down = self.enc_down_dict[v]
+                if self.native_stem and stem.supported(down):
+                    out.append([])
+                else:
+                    out.append(down.conv_stem(image_dict[v], None if masks is None else masks[i]))
+        self._dense_levels = [len(x) for x in out]
+        return out
 
     # -------------------------------------------------------------- forward paths
     def feature_forward(self, image_dict: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
@@ -532,15 +628,19 @@ class CineMA(nn.Module):
             skips = self._stem(views, image_dict, None)
             b = image_dict[views[0]].shape[0]
             dev = image_dict[views[0]].device
-            grids, keep, n_keeps, feats = [], [], [], []
+            grids, keep, n_keeps, masks, slots = [], [], [], [], []
             for i, v in enumerate(views):
                 down = self.enc_down_dict[v]
                 grid = tuple(s // p for s, p in zip(image_dict[v].shape[2:], down.eff_patch_size))
+                n = math.prod(grid)
                 grids.append(grid)
-                n_keeps.append(math.prod(grid))
-                keep.append(engine.arange_idx(b, 0, math.prod(grid), dev))
-                feats.append(skips[i][-1] if skips[i] else image_dict[v].to(F32).contiguous())
-            _, fused, _ = _encode(self, arena, views, feats, skips, keep, n_keeps, grids, b, False, True)
+                n_keeps.append(n)
+                keep.append(engine.arange_idx(b, 0, n, dev))
+                slots.append(keep[-1])  # every token is visible: slot == token id
+                masks.append(torch.zeros((b, n), dtype=torch.bool, device=dev))
+            imgs32 = [image_dict[v].to(F32).contiguous() for v in views]
+            sources, _ = _build_sources(self, arena, views, imgs32, skips, keep, masks, slots, grids, n_keeps, b, False)
+            _, fused, _ = _encode(self, arena, views, sources, keep, n_keeps, b, False, True)
         return fused
 
     def forward(self, image_dict: dict[str, torch.Tensor], enc_mask_ratio: float,

@@ -76,17 +76,20 @@ int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, long long q_
 
 /* ---- LayerNorm (row-wise over the last dim, fp32 statistics) -------------------------- *
  * y = (x - mean) * rstd * gamma + beta.  x fp32 [M,D] (row pitch ldx).  y16 (bf16) and/or y32
- * (fp32) may be NULL.  mean / rstd (fp32 [M]) may be NULL for inference.
+ * (fp32) may be NULL.  mean / rstd (fp32 [M]) may be NULL for inference.  act=1 applies exact-erf GELU to the
+ * normalised output (ConvNormActBlock, cinema/conv.py:257-273).
  * Replaces nn.LayerNorm at cinema/vit.py:549,564,650,738, cinema/convvit.py:254,290 and the
  * permute+LayerNorm+permute of ConvLayerNorm (cinema/conv.py:169-187) on channel-last rows. */
 int cb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, int M, int D, float eps,
-                     void* y16, long long ldy16, float* y32, long long ldy32, float* mean, float* rstd, void* stream);
-/* dx = LN'(dy) (+ dres if given) -> dx32 (fp32) and optional bf16 copy dx16; dgamma / dbeta are
+                     void* y16, long long ldy16, float* y32, long long ldy32, float* mean, float* rstd, int act,
+                     void* stream);
+/* beta_act != NULL: the forward was run with act=1; dy is first multiplied by GELU'(LN output) (needs beta).
+ * dx = LN'(dy) (+ dres if given) -> dx32 (fp32) and optional bf16 copy dx16; dgamma / dbeta are
  * accumulated with fp32 atomics (may be NULL).  dy is bf16 (dy_dtype=CB_DT_BF16) or fp32. */
 int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, const float* x, long long ldx, const float* mean,
                      const float* rstd, const float* gamma, const float* dres, long long lddres, int M, int D,
                      float* dx32, long long lddx32, void* dx16, long long lddx16, float* dgamma, float* dbeta,
-                     void* stream);
+                     const float* beta_act, void* stream);
 
 /* ---- data movement (bit-exact) --------------------------------------------------------- */
 /* fp32 -> bf16 (round-to-nearest-even) over a flat buffer: the per-step bf16 shadow of the weights. */
@@ -165,6 +168,25 @@ int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, const int* spa
  * target_std, normed_target_max, pred_max} of view v; scales[v] = d loss / d (pred - target) factor of view v. */
 int cb_mae_loss_finalize(const float* acc, int n_views, const float* sq_count, const float* patch_count, float* out,
                          float* scales, void* stream);
+
+/* ---- ConvMAE stem on the visible patches only (token-major channel-last rows x[(b, i), p, c]) ------------ *
+ * keep (B, nk) ascending visible token ids, mask (B, n_tok) 1 = removed, slot from cb_mask_to_index.
+ * grid_tok: ViT token grid; f: positions per token and axis at this stem level (e.g. {4,4,1} then {2,2,1}).
+ * out[b, i*P + p] = id of position p of token keep[b,i] in the level grid (grid_tok * f): the index list that lets
+ * cb_gather_patches read the k==s patch-conv inputs of the first stem level straight from the image. */
+int cb_expand_token_index(const int* keep, int B, int nk, int ndim, const int* grid_tok, const int* f, int* out,
+                          void* stream);
+/* Depth-wise 5^ndim convolution, "same" zero padding, bf16 in / out, fp32 accumulation (cinema/conv.py:385,410-411:
+ * dw_conv(mask * x)): neighbours are looked up through the token map, masked or out-of-image neighbours are zero.
+ * w: bf16 (C, 1, 5, 5[, 5]); bias fp32 (C) or NULL.  transpose=1 correlates with the flipped kernel = gradient
+ * with respect to the input. */
+int cb_dwconv_tokens(const void* in, void* out, const void* w, const float* bias, const unsigned char* mask,
+                     const int* slot, const int* keep, int B, int nk, int C, int ndim, const int* grid_tok, const int* f,
+                     int transpose, void* stream);
+/* dw (fp32, (C, 1, 5, 5[, 5])) += sum dy * shifted in;  db (fp32 (C), may be NULL) += sum dy. */
+int cb_dwconv_tokens_wgrad(const void* in, const void* dy, float* dw, float* db, const unsigned char* mask,
+                           const int* slot, const int* keep, int B, int nk, int C, int ndim, const int* grid_tok,
+                           const int* f, void* stream);
 
 /* ---- optimiser step over the flat arena ------------------------------------------------- *
  * out[0] += sum x^2 (global gradient norm, torch.nn.utils.clip_grad_norm_ at cinema/optim.py:206). */

@@ -80,11 +80,13 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale):
     dq.copy_(torch.einsum("bhqk,bkhd->bqhd", ds, k.float()).to(BF16))
 
 
-def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None, act=False):
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     r = torch.rsqrt(var + eps)
     y = (x - mu) * r * gamma + beta
+    if act:
+        y = _gelu(y)
     if y32 is not None:
         y32.copy_(y)
     if y16 is not None:
@@ -95,9 +97,11 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None)
         rstd.copy_(r.squeeze(-1))
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None, beta_act=None):
     d = dy.float()
     xh = (x - mean[:, None]) * rstd[:, None]
+    if beta_act is not None:
+        d = d * _gelu_grad(xh * gamma + beta_act)
     dyg = d * gamma
     m1 = dyg.mean(-1, keepdim=True)
     m2 = (dyg * xh).mean(-1, keepdim=True)
@@ -286,6 +290,66 @@ def rope_apply(x, cos, sin, transpose=False):
     return torch.cat([(head * c + rot * s).to(x.dtype), x[..., ro:]], -1)
 
 
+def expand_token_index(keep, grid_tok, f):
+    b, nk = keep.shape
+    nd = len(f)
+    t = keep.long()
+    tg = []
+    for a in range(nd - 1, -1, -1):
+        tg.insert(0, t % grid_tok[a])
+        t = t // grid_tok[a]
+    p = math.prod(f)
+    pid = torch.arange(p)
+    pa = []
+    for a in range(nd - 1, -1, -1):
+        pa.insert(0, pid % f[a])
+        pid = pid // f[a]
+    idx = torch.zeros(b, nk, p, dtype=torch.long)
+    for a in range(nd):
+        idx = idx * (grid_tok[a] * f[a]) + tg[a][..., None] * f[a] + pa[a]
+    return idx.reshape(b, nk * p).int()
+
+
+def _dense_from_tokens(x, keep, grid_tok, f, c):
+    """(B*nk*P, C) token-major rows -> dense (B, C, *level_grid) with zeros at masked tokens, plus the flat index."""
+    b, nk = keep.shape
+    idx = expand_token_index(keep, grid_tok, f).long()  # (B, nk*P)
+    level = [g * ff for g, ff in zip(grid_tok, f)]
+    dense = torch.zeros(b, math.prod(level), c)
+    dense.scatter_(1, idx[..., None].expand(-1, -1, c), x.float().reshape(b, -1, c))
+    return dense.transpose(1, 2).reshape(b, c, *level), idx, level
+
+
+def dwconv_tokens(x, out, w, bias, mask, slot, keep, grid_tok, f, transpose=False):
+    import torch.nn.functional as F
+
+    c = x.shape[-1]
+    dense, idx, level = _dense_from_tokens(x, keep, grid_tok, f, c)
+    wf = w.float()
+    if transpose:
+        wf = wf.flip(dims=list(range(2, wf.dim())))
+    conv = F.conv2d if len(f) == 2 else F.conv3d
+    y = conv(dense, wf, bias.float() if bias is not None else None, padding=2, groups=c)
+    y = y.reshape(y.shape[0], c, -1).transpose(1, 2)
+    out.copy_(torch.gather(y, 1, idx[..., None].expand(-1, -1, c)).reshape(out.shape).to(BF16))
+
+
+def dwconv_tokens_wgrad(x, dy, dw, db, mask, slot, keep, grid_tok, f):
+    import torch.nn.functional as F
+
+    c = x.shape[-1]
+    dense, idx, level = _dense_from_tokens(x, keep, grid_tok, f, c)
+    ddense, _, _ = _dense_from_tokens(dy, keep, grid_tok, f, c)
+    wz = torch.zeros_like(dw).requires_grad_()
+    conv = F.conv2d if len(f) == 2 else F.conv3d
+    with torch.enable_grad():
+        y = conv(dense, wz, None, padding=2, groups=c)
+        (y * ddense).sum().backward()
+    dw.add_(wz.grad)
+    if db is not None:
+        db.add_(dy.float().sum(0))
+
+
 def sumsq(x, out):
     out[0] += (x.double() ** 2).sum().float()
 
@@ -315,5 +379,5 @@ def device_info():
 ALL = [
     "gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16", "mask_to_index",
     "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize", "patchify",
-    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply", "sumsq", "adamw_flat",
+    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply", "sumsq", "adamw_flat", "expand_token_index", "dwconv_tokens", "dwconv_tokens_wgrad",
 ]

@@ -364,3 +364,100 @@ def test_masked_mse(shape, patch, norm_target):
     if norm_target:
         torch.testing.assert_close(acc[3], t.max(), rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(acc[4], pred.max(), rtol=0, atol=0)
+
+
+# ----------------------------------------------------------------------------- native stem kernels
+def _token_setup(b, grid_tok, keep_frac, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    n = math.prod(grid_tok)
+    nk = max(1, int(n * keep_frac))
+    mask = torch.ones(b, n, dtype=torch.bool, device=DEV)
+    for i in range(b):
+        mask[i, torch.randperm(n, device=DEV, generator=g)[:nk]] = False
+    keep, drop, slot = _C.mask_to_index(mask, nk)
+    return mask, keep, slot, nk
+
+
+def _dense_from_tokens(x, idx, level, c):
+    b = idx.shape[0]
+    dense = torch.zeros(b, math.prod(level), c, device=DEV)
+    dense.scatter_(1, idx.long()[..., None].expand(-1, -1, c), x.float().reshape(b, -1, c))
+    return dense.transpose(1, 2).reshape(b, c, *level)
+
+
+@pytest.mark.parametrize("grid_tok,f,c,keep_frac", [((12, 12, 16), (4, 4, 1), 64, 0.25), ((12, 12, 16), (2, 2, 1), 128, 0.25),
+                                                      ((12, 12), (4, 4), 64, 0.25), ((6, 5), (2, 2), 16, 0.5),
+                                                      ((3, 4, 2), (4, 4, 1), 8, 1.0), ((12, 12), (2, 2), 128, 1.0)])
+def test_dwconv_tokens_fwd_bwd_against_dense_conv(grid_tok, f, c, keep_frac):
+    import torch.nn.functional as F
+
+    b = 2
+    nd = len(f)
+    mask, keep, slot, nk = _token_setup(b, grid_tok, keep_frac, 0)
+    p = math.prod(f)
+    level = [gt * ff for gt, ff in zip(grid_tok, f)]
+    idx = _C.expand_token_index(keep, grid_tok, f)
+    # index expansion against plain arithmetic
+    t = keep.long()
+    coords = []
+    for a in range(nd - 1, -1, -1):
+        coords.insert(0, t % grid_tok[a])
+        t = t // grid_tok[a]
+    pid = torch.arange(p, device=DEV)
+    pa = []
+    for a in range(nd - 1, -1, -1):
+        pa.insert(0, pid % f[a])
+        pid = pid // f[a]
+    ref_idx = torch.zeros(b, nk, p, dtype=torch.long, device=DEV)
+    for a in range(nd):
+        ref_idx = ref_idx * level[a] + coords[a][..., None] * f[a] + pa[a]
+    assert torch.equal(idx.long(), ref_idx.reshape(b, -1))
+
+    x = bf16_randn(b * nk * p, c, seed=1)
+    w = bf16_randn(c, 1, *([5] * nd), scale=0.2, seed=2)
+    bias = torch.randn(c, device=DEV)
+    out = torch.empty_like(x)
+    _C.dwconv_tokens(x, out, w, bias, mask, slot, keep, grid_tok, f)
+    conv = F.conv2d if nd == 2 else F.conv3d
+    dense = _dense_from_tokens(x, idx, level, c)
+    y = conv(dense, w.float(), bias, padding=2, groups=c)
+    y = torch.gather(y.reshape(b, c, -1).transpose(1, 2), 1, idx.long()[..., None].expand(-1, -1, c)).reshape(-1, c)
+    assert rel_err(out, y) < 4e-3  # bf16 output rounding
+    # transpose = gradient w.r.t. the input of the same conv restricted to visible rows
+    dy = bf16_randn(b * nk * p, c, seed=3)
+    dxk = torch.empty_like(dy)
+    _C.dwconv_tokens(dy, dxk, w, None, mask, slot, keep, grid_tok, f, transpose=True)
+    dense_in = dense.clone().requires_grad_()
+    wf = w.float().requires_grad_()
+    yy = conv(dense_in, wf, None, padding=2, groups=c)
+    ddense = _dense_from_tokens(dy, idx, level, c)
+    (yy * ddense).sum().backward()
+    dx_ref = torch.gather(dense_in.grad.reshape(b, c, -1).transpose(1, 2), 1,
+                          idx.long()[..., None].expand(-1, -1, c)).reshape(-1, c)
+    assert rel_err(dxk, dx_ref) < 4e-3
+    dw = torch.zeros(c, 1, *([5] * nd), device=DEV)
+    db = torch.zeros(c, device=DEV)
+    _C.dwconv_tokens_wgrad(x, dy, dw, db, mask, slot, keep, grid_tok, f)
+    assert rel_err(dw, wf.grad) < 1e-4
+    assert rel_err(db, dy.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("m,d", [(300, 64), (77, 128), (33, 16)])
+def test_layernorm_gelu_fwd_bwd(m, d):
+    x = torch.randn(m, d, device=DEV) * 2 + 0.3
+    gamma, beta = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV) * 0.2
+    y32 = torch.empty(m, d, device=DEV)
+    mean, rstd = torch.empty(m, device=DEV), torch.empty(m, device=DEV)
+    _C.layernorm_fwd(x, gamma, beta, 1e-6, y32=y32, mean=mean, rstd=rstd, act=True)
+    xr = x.clone().requires_grad_()
+    gr, br = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-6))
+    torch.testing.assert_close(y32, ref, rtol=1e-5, atol=2e-6)
+    dy = torch.randn(m, d, device=DEV)
+    (ref * dy).sum().backward()
+    dx = torch.empty(m, d, device=DEV)
+    dg, dbt = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    _C.layernorm_bwd(dy, x, mean, rstd, gamma, dx32=dx, dgamma=dg, dbeta=dbt, beta_act=beta)
+    torch.testing.assert_close(dx, xr.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dg, gr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dbt, br.grad, rtol=1e-4, atol=1e-4)

@@ -42,11 +42,13 @@ def _oracle_autocast(g):
     return loss.detach(), {k: v.detach().float() for k, v in preds.items()}, {k: p.grad for k, p in params.items() if p.grad is not None}
 
 
+@pytest.mark.parametrize("native_stem", [True, False])
 @pytest.mark.parametrize("case", ["mae_small_4view", "mae_hd_selfattn_normtarget"])
-def test_mae_step_parity(case, golden_dir):
+def test_mae_step_parity(case, native_stem, golden_dir):
     g = torch.load(golden_dir / f"{case}.pt")
     model = CineMA(**g["kw"]).to(DEV)
     model.load_state_dict(g["state_dict"])
+    model.native_stem = native_stem
     model.train()
     loss, preds, masks, metrics = model(_to(g["images"], DEV), g["ratio"], enc_mask_dict=_to(g["masks"], DEV))
     loss.backward()
@@ -193,7 +195,7 @@ def test_trainer_graph_equals_eager_and_learns(golden_dir):
     assert losses[True][-1] < losses[True][0]  # the fixed batch is being fit
     # the replayed graph runs the same kernels as the eager step; masks come from the same RNG stream
     # only up to the capture point, so compare the eager prefix exactly and the level afterwards
-    assert losses[True][:2] == losses[False][:2]
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(losses[True][:2], losses[False][:2]))  # atomics reorder sums
     assert abs(losses[True][-1] - losses[False][-1]) < 0.1 * losses[False][0]
 
 

@@ -55,6 +55,27 @@ def test_mae_forward_backward_matches_reference_golden(case, golden_dir, emulate
         assert (p.grad is not None) == p.requires_grad, k
 
 
+@pytest.mark.parametrize("case", ["mae_small_4view"])
+def test_dense_stem_path_matches_too(case, golden_dir, emulated_kernels):
+    """``native_stem=False`` keeps the reference evaluation order (dense conv stem, then gather); same results."""
+    g = torch.load(golden_dir / f"{case}.pt")
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    model.native_stem = False
+    model.train()
+    loss, preds, _, _ = model(g["images"], g["ratio"], enc_mask_dict=g["masks"])
+    assert model._dense_levels == [2, 2, 2, 2]
+    assert abs(float(loss) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, ref in g["grads"].items():
+        assert rel(named[k].grad, ref) < 3e-2, k
+    model.native_stem = True
+    model.zero_grad()
+    model(g["images"], g["ratio"], enc_mask_dict=g["masks"])
+    assert model._dense_levels == [0, 0, 0, 0]
+
+
 @pytest.mark.parametrize("case", ["mae_tiny_sax", "mae_small_4view"])
 def test_feature_forward_matches_reference_golden(case, golden_dir, emulated_kernels):
     g = torch.load(golden_dir / f"{case}.pt")
