@@ -182,6 +182,263 @@ dwconv_wgrad_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dy, fl
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path: square in-plane token blocks F x F (x 1), F in {2, 4}, channels in groups of 64.
+// One WARP per (visible token, 64-channel group): lane = channel pair.  Every neighbour row is one coalesced
+// 128-byte read from L2 (the level tensor is <= 40 MB and L2-resident); the 3 x 3 in-plane neighbour tokens are
+// resolved once per z-plane by nine lanes (mask + slot lookup) and broadcast with shuffles, so the inner loops
+// are fully unrolled register FMAs: (F+4) row loads feed F * 25 FMAs each.
+// ------------------------------------------------------------------------------------------------------------
+template <int F>
+struct Fast {
+  static constexpr int EXT = F + 2 * HALO;
+  __host__ __device__ static constexpr int off(int r) { return (r - HALO + F) / F - 1; }  // neighbour token offset
+  __host__ __device__ static constexpr int pin(int r) { return (r - HALO + F) % F; }      // position inside it
+};
+
+// nb[j] (j = (o0+1)*3 + (o1+1)) = first row of neighbour token (t0+o0, t1+o1, z) in the level tensor, or -1
+template <int ND>
+__device__ __forceinline__ void neighbour_rows(const DwGeom& g, const unsigned char* __restrict__ mask,
+                                               const int* __restrict__ slot, int b, int t0, int t1, int z, int lane,
+                                               int (&nb)[9]) {
+  int mine = -1;
+  if (lane < 9) {
+    const int a0 = t0 + lane / 3 - 1, a1 = t1 + lane % 3 - 1;
+    if (a0 >= 0 && a0 < g.gt[0] && a1 >= 0 && a1 < g.gt[1]) {
+      const int tok = ND == 3 ? (a0 * g.gt[1] + a1) * g.gt[2] + z : a0 * g.gt[1] + a1;
+      const long long mt = (long long)b * g.n_tok + tok;
+      if (mask[mt] == 0) mine = (b * g.nk + slot[mt]) * g.P;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) nb[j] = __shfl_sync(0xffffffffu, mine, j);
+}
+
+template <int F>
+__device__ __forceinline__ void load_row(const bf16* __restrict__ in, const int (&nb)[9], int r0, int C, int coff,
+                                         float2 (&x)[F + 2 * HALO]) {
+  using T = Fast<F>;
+  // r0 is a compile-time constant at every call site (fully unrolled callers)
+#pragma unroll
+  for (int r1 = 0; r1 < T::EXT; ++r1) {
+    const int base = nb[(T::off(r0) + 1) * 3 + T::off(r1) + 1];
+    x[r1] = make_float2(0.f, 0.f);
+    if (base >= 0) {
+      const long long row = (long long)base + T::pin(r0) * F + T::pin(r1);
+      x[r1] = unpack_bf16(__ldg(reinterpret_cast<const unsigned int*>(in + row * C + coff)));
+    }
+  }
+}
+
+template <int F, int ND>
+__global__ void __launch_bounds__(256)
+dwconv_fast_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const bf16* __restrict__ w,
+                   const float* __restrict__ bias, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
+                   const int* __restrict__ keep, DwGeom g, int flip) {
+  using T = Fast<F>;
+  constexpr int E2 = ND == 3 ? KS : 1;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* wsm = reinterpret_cast<bf16*>(smem);  // [taps][C], already flipped for the transposed conv
+  for (int e = threadIdx.x; e < g.taps * g.C; e += blockDim.x) {
+    const int c = e / g.taps, tap = e - c * g.taps;
+    wsm[(flip ? g.taps - 1 - tap : tap) * g.C + c] = w[e];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int cgn = g.C >> 6;
+  const long long n_tasks = (long long)g.B * g.nk * cgn;
+  for (long long task = (long long)blockIdx.x * warps + (threadIdx.x >> 5); task < n_tasks;
+       task += (long long)gridDim.x * warps) {
+    const long long item = task / cgn;
+    const int coff = (int)(task - item * cgn) * 64 + lane * 2;
+    const int b = (int)(item / g.nk);
+    int t = keep[item];
+    int t2 = 0;
+    if (ND == 3) t2 = t % g.gt[2], t /= g.gt[2];
+    const int t1 = t % g.gt[1], t0 = t / g.gt[1];
+    float2 acc[F][F];
+    {
+      float2 b0 = make_float2(0.f, 0.f);
+      if (bias != nullptr) b0 = *reinterpret_cast<const float2*>(bias + coff);
+#pragma unroll
+      for (int i = 0; i < F; ++i)
+#pragma unroll
+        for (int j = 0; j < F; ++j) acc[i][j] = b0;
+    }
+#pragma unroll 1
+    for (int d2 = 0; d2 < E2; ++d2) {
+      const int z = t2 + d2 - (ND == 3 ? HALO : 0);
+      if (ND == 3 && (z < 0 || z >= g.gt[2])) continue;
+      int nb[9];
+      neighbour_rows<ND>(g, mask, slot, b, t0, t1, z, lane, nb);
+      float2 wr[KS * KS];
+#pragma unroll
+      for (int k = 0; k < KS * KS; ++k)
+        wr[k] = unpack_bf16(*reinterpret_cast<const unsigned int*>(wsm + (size_t)(k * E2 + d2) * g.C + coff));
+#pragma unroll
+      for (int r0 = 0; r0 < T::EXT; ++r0) {
+        float2 x[T::EXT];
+        load_row<F>(in, nb, r0, g.C, coff, x);
+#pragma unroll
+        for (int d0 = 0; d0 < KS; ++d0) {
+          const int i0 = r0 - d0;
+          if (i0 < 0 || i0 >= F) continue;
+#pragma unroll
+          for (int d1 = 0; d1 < KS; ++d1)
+#pragma unroll
+            for (int i1 = 0; i1 < F; ++i1) {
+              acc[i0][i1].x = fmaf(wr[d0 * KS + d1].x, x[i1 + d1].x, acc[i0][i1].x);
+              acc[i0][i1].y = fmaf(wr[d0 * KS + d1].y, x[i1 + d1].y, acc[i0][i1].y);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int i0 = 0; i0 < F; ++i0)
+#pragma unroll
+      for (int i1 = 0; i1 < F; ++i1)
+        *reinterpret_cast<unsigned int*>(out + (item * g.P + i0 * F + i1) * g.C + coff) = pack_bf16(acc[i0][i1].x, acc[i0][i1].y);
+  }
+}
+
+// Weight gradient, fast path.  A warp owns one (z-plane d2, 64-channel group) for its whole life and keeps the 25
+// in-plane taps of its channel pair in registers while it strides over the visible tokens; the block then merges
+// its warps in shared memory (layout == global dw) and issues coalesced fp32 reductions.
+template <int F, int ND>
+__global__ void __launch_bounds__(320)
+dwconv_wgrad_fast_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dy, float* __restrict__ dw,
+                         float* __restrict__ db, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
+                         const int* __restrict__ keep, DwGeom g) {
+  using T = Fast<F>;
+  constexpr int E2 = ND == 3 ? KS : 1;
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* dws = reinterpret_cast<float*>(smem);  // [C][taps]
+  float* dbs = dws + (size_t)g.C * g.taps;      // [C]
+  for (int e = threadIdx.x; e < g.C * g.taps + g.C; e += blockDim.x) dws[e] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const int cgn = g.C >> 6;
+  const int combos = E2 * cgn;            // host: warps % combos == 0
+  const int combo = warp % combos;
+  const int d2 = combo % E2;
+  const int coff = (combo / E2) * 64 + lane * 2;
+  const int streams_per_block = warps / combos;
+  const long long n_items = (long long)g.B * g.nk;
+  float2 acc[KS * KS];
+#pragma unroll
+  for (int k = 0; k < KS * KS; ++k) acc[k] = make_float2(0.f, 0.f);
+  float2 accb = make_float2(0.f, 0.f);
+  const bool bias_warp = db != nullptr && d2 == (ND == 3 ? HALO : 0);
+  for (long long item = (long long)blockIdx.x * streams_per_block + warp / combos; item < n_items;
+       item += (long long)gridDim.x * streams_per_block) {
+    const int b = (int)(item / g.nk);
+    int t = keep[item];
+    int t2 = 0;
+    if (ND == 3) t2 = t % g.gt[2], t /= g.gt[2];
+    const int t1 = t % g.gt[1], t0 = t / g.gt[1];
+    const int z = t2 + d2 - (ND == 3 ? HALO : 0);
+    if (ND == 3 && (z < 0 || z >= g.gt[2])) continue;
+    int nb[9];
+    neighbour_rows<ND>(g, mask, slot, b, t0, t1, z, lane, nb);
+    float2 d[F][F];
+#pragma unroll
+    for (int i0 = 0; i0 < F; ++i0)
+#pragma unroll
+      for (int i1 = 0; i1 < F; ++i1)
+        d[i0][i1] = unpack_bf16(__ldg(reinterpret_cast<const unsigned int*>(dy + (item * g.P + i0 * F + i1) * g.C + coff)));
+    if (bias_warp) {
+#pragma unroll
+      for (int i0 = 0; i0 < F; ++i0)
+#pragma unroll
+        for (int i1 = 0; i1 < F; ++i1) accb.x += d[i0][i1].x, accb.y += d[i0][i1].y;
+    }
+#pragma unroll
+    for (int r0 = 0; r0 < T::EXT; ++r0) {
+      float2 x[T::EXT];
+      load_row<F>(in, nb, r0, g.C, coff, x);
+#pragma unroll
+      for (int d0 = 0; d0 < KS; ++d0) {
+        const int i0 = r0 - d0;
+        if (i0 < 0 || i0 >= F) continue;
+#pragma unroll
+        for (int d1 = 0; d1 < KS; ++d1)
+#pragma unroll
+          for (int i1 = 0; i1 < F; ++i1) {
+            acc[d0 * KS + d1].x = fmaf(d[i0][i1].x, x[i1 + d1].x, acc[d0 * KS + d1].x);
+            acc[d0 * KS + d1].y = fmaf(d[i0][i1].y, x[i1 + d1].y, acc[d0 * KS + d1].y);
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KS * KS; ++k) {
+    atomicAdd(dws + (size_t)coff * g.taps + k * E2 + d2, acc[k].x);
+    atomicAdd(dws + (size_t)(coff + 1) * g.taps + k * E2 + d2, acc[k].y);
+  }
+  if (bias_warp) {
+    atomicAdd(dbs + coff, accb.x);
+    atomicAdd(dbs + coff + 1, accb.y);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < g.C * g.taps; e += blockDim.x) atomicAdd(dw + e, dws[e]);
+  if (db != nullptr)
+    for (int e = threadIdx.x; e < g.C; e += blockDim.x) atomicAdd(db + e, dbs[e]);
+}
+
+// 0 = not covered by the fast path
+inline int fast_f(const DwGeom& g) {
+  if (g.C % 64 != 0 || g.f[0] != g.f[1] || g.f[2] != 1) return 0;
+  return (g.f[0] == 2 || g.f[0] == 4) ? g.f[0] : 0;
+}
+
+template <int F, int ND>
+int launch_fast_fwd(const void* in, void* out, const void* w, const float* bias, const unsigned char* mask,
+                    const int* slot, const int* keep, const DwGeom& g, int transpose, cudaStream_t stream) {
+  const size_t smem = (size_t)g.taps * g.C * sizeof(bf16);
+  auto kern = dwconv_fast_kernel<F, ND>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long tasks = (long long)g.B * g.nk * (g.C / 64);
+  long long blocks = (tasks + 7) / 8;
+  const long long cap = (long long)cb_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, 256, smem, stream>>>((const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot, keep, g,
+                                               transpose);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int F, int ND>
+int launch_fast_wgrad(const void* in, const void* dy, float* dw, float* db, const unsigned char* mask, const int* slot,
+                      const int* keep, const DwGeom& g, cudaStream_t stream) {
+  const int combos = (ND == 3 ? KS : 1) * (g.C / 64);
+  if (combos > 10) return -2;  // caller falls back to the generic kernel
+  const int warps = combos * (10 / combos);
+  const size_t smem = ((size_t)g.C * g.taps + g.C) * sizeof(float);
+  if (smem > 200 * 1024) return -2;
+  auto kern = dwconv_wgrad_fast_kernel<F, ND>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const long long items = (long long)g.B * g.nk;
+  const int spb = warps / combos;
+  long long blocks = (items + spb - 1) / spb;
+  const long long cap = (long long)cb_sm_count() * 2;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>((const bf16*)in, (const bf16*)dy, dw, db, mask, slot, keep, g);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
 // out[b, i*P + p] = flattened position id, in the level grid (gt * f), of position p of visible token keep[b, i]
 __global__ void expand_index_kernel(const int* __restrict__ keep, long long n_items, DwGeom g, int* __restrict__ out) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,6 +488,13 @@ extern "C" int cb_dwconv_tokens(const void* in, void* out, const void* w, const 
   if (int rc = fill(g, B, nk, C, ndim, grid_tok, f)) return rc;
   if ((long long)B * nk <= 0) return 0;
   CB_CHECK_ARG(C % 8 == 0, "dwconv: C=%d must be a multiple of 8", C);
+  if (const int ff = fast_f(g)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ff == 4) return ndim == 3 ? launch_fast_fwd<4, 3>(in, out, w, bias, mask, slot, keep, g, transpose, st)
+                                  : launch_fast_fwd<4, 2>(in, out, w, bias, mask, slot, keep, g, transpose, st);
+    return ndim == 3 ? launch_fast_fwd<2, 3>(in, out, w, bias, mask, slot, keep, g, transpose, st)
+                     : launch_fast_fwd<2, 2>(in, out, w, bias, mask, slot, keep, g, transpose, st);
+  }
   const size_t smem = ((size_t)g.taps + g.R) * C * sizeof(bf16);
   CB_CHECK_ARG(smem <= 220 * 1024, "dwconv: tile of %zu bytes does not fit in shared memory", smem);
   static size_t configured = 0;
@@ -253,6 +517,15 @@ extern "C" int cb_dwconv_tokens_wgrad(const void* in, const void* dy, float* dw,
   if (int rc = fill(g, B, nk, C, ndim, grid_tok, f)) return rc;
   if ((long long)B * nk <= 0) return 0;
   CB_CHECK_ARG(C % 8 == 0 && C <= 512, "dwconv_wgrad: C=%d must be a multiple of 8 and <= 512", C);
+  if (const int ff = fast_f(g)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (ff == 4) rc = ndim == 3 ? launch_fast_wgrad<4, 3>(in, dy, dw, db, mask, slot, keep, g, st)
+                                : launch_fast_wgrad<4, 2>(in, dy, dw, db, mask, slot, keep, g, st);
+    else rc = ndim == 3 ? launch_fast_wgrad<2, 3>(in, dy, dw, db, mask, slot, keep, g, st)
+                        : launch_fast_wgrad<2, 2>(in, dy, dw, db, mask, slot, keep, g, st);
+    if (rc != -2) return rc;
+  }
   const int c2n = C / 2;
   const int groups = 256 / c2n;
   CB_CHECK_ARG(groups >= 1 && (g.taps + groups - 1) / groups <= MAX_TAPS_PER_THREAD,

@@ -79,7 +79,7 @@ class MAETrainer:
 
     def __init__(self, model: nn.Module, *, lr: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.05,
                  clip_grad: float | None = 5.0, enc_mask_ratio: float = 0.75, use_cuda_graph: bool = True,
-                 process_group=None, graph_warmup: int = 3) -> None:
+                 process_group=None, graph_warmup: int = 2) -> None:
         self.model = model
         self.ratio = enc_mask_ratio
         self.pg = process_group

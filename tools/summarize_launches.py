@@ -1,0 +1,75 @@
+"""Summarise an ``ncu --metrics gpu__time_duration.sum --csv`` launch list into a per-kernel table of ONE step.
+
+    python tools/summarize_launches.py gpurun_out/launches.csv [--out profiles/r01_launches.md] [--title "..."]
+
+The step is delimited by the optimiser kernel (``adamw_kernel``): everything after the previous step's last
+``adamw_kernel`` launch up to and including this step's last one.  Times are ncu's serialised cold-cache
+durations: compare SHARES, not absolutes (B200_PROFILING.md).
+"""
+
+from __future__ import annotations
+
+import argparse
+import csv
+import io
+import re
+from collections import OrderedDict
+
+
+def short(name: str) -> str:
+    name = re.sub(r"\(anonymous namespace\)::", "", name)
+    name = re.sub(r"^void ", "", name)
+    m = re.match(r"([A-Za-z0-9_:]+(<[^()]*>)?)", name)
+    s = m.group(1) if m else name
+    s = s.replace("at::native::", "at::")
+    return s[:110]
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("csv")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--title", default="kernel launches of one step")
+    ap.add_argument("--marker", default="adamw_kernel")
+    ap.add_argument("--step", type=int, default=-1, help="which step (index into marker-delimited steps)")
+    a = ap.parse_args()
+    text = open(a.csv, errors="replace").read()
+    start = text.find('"ID"')
+    rows = list(csv.DictReader(io.StringIO(text[start:])))
+    launches = []
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        ns = v * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1.0)
+        launches.append((r["Kernel Name"], ns))
+    marks = [i for i, (n, _) in enumerate(launches) if a.marker in n]
+    # group consecutive marker launches (segments of the arena) into step ends
+    ends = [m for j, m in enumerate(marks) if j + 1 == len(marks) or marks[j + 1] - m > 8]
+    if len(ends) >= 2:
+        idx = a.step if a.step >= 0 else len(ends) - 1
+        lo, hi = ends[idx - 1] + 1, ends[idx] + 1
+    else:
+        lo, hi = 0, len(launches)
+    step = launches[lo:hi]
+    agg: "OrderedDict[str, list[float]]" = OrderedDict()
+    for n, ns in step:
+        e = agg.setdefault(short(n), [0.0, 0])
+        e[0] += ns
+        e[1] += 1
+    total = sum(v[0] for v in agg.values())
+    lines = [f"# {a.title}", "",
+             f"{len(step)} launches, {total / 1e6:.3f} ms summed ncu durations (serialised, cold cache: compare shares). "
+             f"{len(ends)} steps found in the capture; launches {lo}..{hi} shown.", "",
+             "| kernel | launches | total ms | share | avg us |", "|---|---:|---:|---:|---:|"]
+    for n, (ns, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        lines.append(f"| `{n}` | {c} | {ns / 1e6:.3f} | {100 * ns / total:.1f}% | {ns / c / 1e3:.1f} |")
+    out = "\n".join(lines) + "\n"
+    if a.out:
+        open(a.out, "w").write(out)
+    print(out)
+
+
+if __name__ == "__main__":
+    main()
