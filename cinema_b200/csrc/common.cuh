@@ -83,6 +83,33 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return fmaf(x, pdf, cdf);
 }
+// single-instruction MUFU forms (no IEEE slow path, so the compiler can interleave independent chains)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Normal CDF for the GEMM epilogues, where instruction issue is the budget: Phi(x) = 1 / (1 + 2^(x * P(x^2))) with a
+// degree-4 minimax P (log2(e) folded in); |abs err| < 1.6e-6 on the whole real line (tools/fit_phi.py), i.e. far
+// below the bf16 rounding of the outputs it feeds.  One MUFU.EX2 + one MUFU.RCP, 6 FMA-pipe instructions.
+__device__ __forceinline__ float phi_fast(float x) {
+  const float x2 = x * x;
+  float p = fmaf(x2, -4.11170731e-06f, 1.05875057e-04f);
+  p = fmaf(p, x2, 2.53413164e-04f);
+  p = fmaf(p, x2, -1.05005942e-01f);
+  p = fmaf(p, x2, -2.30216527e+00f);
+  return rcp_approx(1.0f + ex2_approx(x * p));
+}
+__device__ __forceinline__ float gelu_fast(float x) { return x * phi_fast(x); }
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, phi_fast(x));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -12,8 +12,8 @@
 // Replaces the cuBLASLt calls behind nn.Linear at cinema/vit.py:472-477, timm Mlp (cinema/vit.py:570-575),
 // cinema/mae/mae.py:395,435-440 and cinema/convvit.py:121,294-298 of the reference.
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..9 epilogue
-// (two warps per TMEM lane quarter, each owning half of the tile's columns).  Two TMEM accumulator
+// CTA = 576 threads: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..17 epilogue
+// (four warps per TMEM lane quarter, each owning a quarter of the tile's columns).  Two TMEM accumulator
 // stages let the epilogue of tile i overlap the main loop of tile i+1.
 #include "../../include/cinema_b200.h"
 #include "common.cuh"
@@ -22,8 +22,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NUM_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
+constexpr int NUM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct GemmArgs {
   int M, N, K;
@@ -49,7 +49,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 2048;  // per-warp 32 x 16 fp32 epilogue transposition tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -62,7 +63,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -181,89 +182,114 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncwarp();
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;            // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns
-    constexpr int COLS_PER_WARP = BN / 2;
-    constexpr int CHUNKS = COLS_PER_WARP / 32;
+    // 16 warps: four per TMEM lane quarter, each owning a quarter of the tile's columns in chunks of 16.
+    // TMEM -> registers (thread == accumulator row) -> per-warp swizzled smem tile -> registers in a row-coalesced
+    // layout (4 lanes x 16 B cover 64 B of one row, 8 rows per instruction), so that every global access of the
+    // epilogue (bias, residual, GELU' input, fp32 / bf16 stores, split-K reductions) moves whole 32-byte sectors.
+    // Residual / GELU' operands of chunk c+1 are fetched into registers before the math of chunk c (and those of
+    // a tile's first chunk before the wait on its accumulator), which hides their latency behind the main loop.
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quarter this warp may touch
+    const int cq = ew >> 2;    // which quarter of the tile's columns
+    constexpr int COLS_PER_WARP = BN / 4;
+    constexpr int CHUNKS = COLS_PER_WARP / 16;
+    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + ew * 2048);
+    const int sub = lane >> 2;  // row inside a group of eight
+    const int c16 = lane & 3;   // 16-byte column (4 fp32) inside the 16-column chunk
+    const bool has_res = p.residual != nullptr;
+    const bool has_aux = p.epi == CB_EPI_GELU_BWD;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4 pre_res[4];
+    uint2 pre_aux[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre_res[i] = make_float4(0.f, 0.f, 0.f, 0.f), pre_aux[i] = make_uint2(0u, 0u);
+    auto prefetch = [&](long long row_base, int col) {
+      if (col >= p.N) return;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = row_base + i * 8 + sub;
+        if (row < p.M) {
+          if (has_res) pre_res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
+          if (has_aux) pre_aux[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col));
+        }
+      }
+    };
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int tile = item / p.splits;
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
+      const long long row_base = (long long)m_tile * BM + q * 32;
+      const int colw = n_tile * BN + cq * COLS_PER_WARP + c16 * 4;  // this lane's first column in chunk 0
+      if (has_res || has_aux) prefetch(row_base, colw);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const long long row = (long long)m_tile * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = n_tile * BN + half * COLS_PER_WARP + c * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr, r);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cq * COLS_PER_WARP + c * 16;
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr, r);
         tmem_ld_wait();
-        if (col0 >= p.N || !row_ok) continue;
-        float v[32];
+        long long rb = row_base;
+        asm volatile("" : "+l"(rb));  // keep the per-row address arithmetic inside the chunk loop (register pressure)
+        const int col = colw + c * 16;
+        const bool col_ok = col < p.N;  // N is a multiple of 8
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                       "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        float x[4][4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // groups of 8 columns (N is a multiple of 8)
-          const int col = col0 + g * 8;
-          if (col >= p.N) break;
-          float* x = v + g * 8;
-          if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-            x[0] += b0.x, x[1] += b0.y, x[2] += b0.z, x[3] += b0.w;
-            x[4] += b1.x, x[5] += b1.y, x[6] += b1.z, x[7] += b1.w;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + sub;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x[i][0]), "=f"(x[i][1]), "=f"(x[i][2]), "=f"(x[i][3])
+                       : "r"(stg + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4)));
+        }
+        __syncwarp();  // staging tile is rewritten by the next chunk
+        float4 res[4];
+        uint2 aux[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res[i] = pre_res[i], aux[i] = pre_aux[i];
+        if ((has_res || has_aux) && c + 1 < CHUNKS) prefetch(rb, col + 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long row = rb + i * 8 + sub;
+          if (row >= p.M || !col_ok) continue;
+          float* v = x[i];
+          v[0] = fmaf(v[0], p.alpha, bias4.x), v[1] = fmaf(v[1], p.alpha, bias4.y);
+          v[2] = fmaf(v[2], p.alpha, bias4.z), v[3] = fmaf(v[3], p.alpha, bias4.w);
           if (p.epi == CB_EPI_GELU) {
             // pre-activation is rounded to bf16 first (what autocast feeds nn.GELU), saved for backward
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
-            if (p.out != nullptr) {
-              uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                   pack_bf16(x[6], x[7]));
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_f(x[j]);
-            uint4 o2 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                  pack_bf16(x[6], x[7]));
-            *reinterpret_cast<uint4*>(p.out2 + row * p.ldo2 + col) = o2;
+            const uint2 pre = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            if (p.out != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = pre;
+            const float2 p0 = unpack_bf16(pre.x), p1 = unpack_bf16(pre.y);
+            *reinterpret_cast<uint2*>(p.out2 + row * p.ldo2 + col) =
+                make_uint2(pack_bf16(gelu_fast(p0.x), gelu_fast(p0.y)), pack_bf16(gelu_fast(p1.x), gelu_fast(p1.y)));
             continue;
           }
-          if (p.epi == CB_EPI_GELU_BWD) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + col));
-            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-            x[0] *= gelu_grad_f(a0.x), x[1] *= gelu_grad_f(a0.y), x[2] *= gelu_grad_f(a1.x), x[3] *= gelu_grad_f(a1.y);
-            x[4] *= gelu_grad_f(a2.x), x[5] *= gelu_grad_f(a2.y), x[6] *= gelu_grad_f(a3.x), x[7] *= gelu_grad_f(a3.y);
+          if (has_aux) {
+            const float2 a0 = unpack_bf16(aux[i].x), a1 = unpack_bf16(aux[i].y);
+            v[0] *= gelu_grad_fast(a0.x), v[1] *= gelu_grad_fast(a0.y);
+            v[2] *= gelu_grad_fast(a1.x), v[3] *= gelu_grad_fast(a1.y);
           }
-          if (p.residual != nullptr) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
-            const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col + 4));
-            x[0] += r0.x, x[1] += r0.y, x[2] += r0.z, x[3] += r0.w;
-            x[4] += r1.x, x[5] += r1.y, x[6] += r1.z, x[7] += r1.w;
-          }
+          if (has_res) v[0] += res[i].x, v[1] += res[i].y, v[2] += res[i].z, v[3] += res[i].w;
           if (p.out_fp32) {
             float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-            if (p.atomic_add) {
-              red_add_v4(o, x[0], x[1], x[2], x[3]);
-              red_add_v4(o + 4, x[4], x[5], x[6], x[7]);
-            } else {
-              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
+            if (p.atomic_add)
+              red_add_v4(o, v[0], v[1], v[2], v[3]);
+            else
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
           } else {
-            uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                 pack_bf16(x[6], x[7]));
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = o;
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) =
+                make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
           }
-          if (p.out2 != nullptr) {  // optional bf16 shadow of an fp32 result
-            uint4 o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                 pack_bf16(x[6], x[7]));
-            *reinterpret_cast<uint4*>(p.out2 + row * p.ldo2 + col) = o;
-          }
+          if (p.out2 != nullptr)  // optional bf16 shadow of an fp32 result
+            *reinterpret_cast<uint2*>(p.out2 + row * p.ldo2 + col) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
         }
       }
       tcgen05_fence_before();

@@ -1,5 +1,6 @@
-"""Micro-benchmark of cb_gemm_bf16 against torch.matmul (cuBLAS) on the shapes of the ViT-B MAE step.
-Run on the GPU box: python tools/perf_gemm.py"""
+"""Micro-benchmark of cb_gemm_bf16 against torch.matmul (cuBLAS) on the dominant shapes of the ViT-B MAE step
+(tools/gemm_shapes.py).  Run on the GPU box: python tools/perf_gemm.py [--bn 0]"""
+import argparse
 import sys
 from pathlib import Path
 
@@ -11,7 +12,7 @@ from cinema_b200 import _C  # noqa: E402
 DEV = "cuda"
 
 
-def timeit(fn, iters=20, warm=5):
+def timeit(fn, iters=12, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -30,46 +31,55 @@ def timeit(fn, iters=20, warm=5):
 
 
 def main():
-    B = 16
-    shapes = []
-    for tag, tok, d in [("enc", 769, 768), ("dec", 2305, 512)]:
-        m = B * tok
-        shapes += [(f"{tag}.qkv/fc-like", m, 3 * d, d), (f"{tag}.proj", m, d, d), (f"{tag}.fc1", m, 4 * d, d),
-                   (f"{tag}.fc2", m, d, 4 * d)]
-    print(f"{'shape':22s} {'M':>6s} {'N':>5s} {'K':>5s} | {'fwd us':>8s} {'TF/s':>7s} {'cublas':>7s} | {'dgrad':>7s} {'TF/s':>6s} | {'wgrad':>7s} {'TF/s':>6s} {'cublas':>7s}")
-    for name, m, n, k in shapes:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bn", type=int, default=0)
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    # (name, M, N, K) forward orientation y[M,N] = x[M,K] w[N,K]^T ; count per step
+    shapes = [("enc.fc1 gelu", 10960, 3072, 768, 12), ("enc.fc2 res", 10960, 768, 3072, 12), ("enc.qkv", 10960, 2304, 768, 12),
+              ("enc.proj res", 10960, 768, 768, 12), ("dec.fc1 gelu", 32848, 2048, 512, 8), ("dec.fc2 res", 32848, 512, 2048, 8),
+              ("dec.q/proj", 32848, 512, 512, 16), ("dec.kv_all", 10944, 8192, 512, 1)]
+    if a.quick:
+        shapes = shapes[:2]
+    print(f"{'shape':14s} {'M':>6s} {'N':>5s} {'K':>5s} | {'fwd us':>7s} {'TF/s':>6s} {'cublas':>6s} | {'dgrad':>7s} {'TF/s':>6s} {'cublas':>6s} | {'wgrad':>7s} {'TF/s':>6s} {'cublas':>6s} | step ms")
+    total = 0.0
+    for name, m, n, k, cnt in shapes:
         x = torch.randn(m, k, device=DEV).bfloat16()
         w = (torch.randn(n, k, device=DEV) * 0.02).bfloat16()
         dy = torch.randn(m, n, device=DEV).bfloat16()
+        bias = torch.randn(n, device=DEV)
         y = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        y2 = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        y32 = torch.empty(m, n, device=DEV)
+        res = torch.randn(m, n, device=DEV)
         dx = torch.empty(m, k, device=DEV, dtype=torch.bfloat16)
+        aux = torch.randn(m, k, device=DEV).bfloat16()
         dw = torch.zeros(n, k, device=DEV)
         fl = 2.0 * m * n * k
-        t_f = timeit(lambda: _C.gemm(x, w, y))
+        if "gelu" in name:
+            f_fwd = lambda: _C.gemm(x, w, y, out2=y2, bias=bias, epilogue=_C.EPI_GELU, block_n=a.bn)
+            f_dg = lambda: _C.gemm(dy, w, dx, b_mn=True, block_n=a.bn)
+        elif "res" in name:
+            f_fwd = lambda: _C.gemm(x, w, y32, bias=bias, residual=res, block_n=a.bn)
+            # dgrad of fc2 / proj feeds GELU' (fc2) -- time the GELU' variant for fc2
+            if "fc2" in name:
+                f_dg = lambda: _C.gemm(dy, w, dx, b_mn=True, aux=aux, epilogue=_C.EPI_GELU_BWD, block_n=a.bn)
+            else:
+                f_dg = lambda: _C.gemm(dy, w, dx, b_mn=True, block_n=a.bn)
+        else:
+            f_fwd = lambda: _C.gemm(x, w, y, bias=bias, block_n=a.bn)
+            f_dg = lambda: _C.gemm(dy, w, dx, b_mn=True, block_n=a.bn)
+        t_f = timeit(f_fwd)
         t_c = timeit(lambda: torch.matmul(x, w.t()))
-        t_d = timeit(lambda: _C.gemm(dy, w, dx, b_mn=True))
+        t_d = timeit(f_dg)
+        t_dc = timeit(lambda: torch.matmul(dy, w))
         t_w = timeit(lambda: _C.gemm(dy, x, dw, a_mn=True, b_mn=True, accumulate=True))
         t_wc = timeit(lambda: torch.matmul(dy.t(), x))
         tf = lambda t: fl / t / 1e9  # noqa: E731
-        print(f"{name:22s} {m:6d} {n:5d} {k:5d} | {t_f*1e3:8.1f} {tf(t_f):7.0f} {tf(t_c):7.0f} | {t_d*1e3:7.1f} {tf(t_d):6.0f} | {t_w*1e3:7.1f} {tf(t_w):6.0f} {tf(t_wc):7.0f}")
-    # epilogue variants on the fc1 shape
-    m, n, k = B * 769, 3072, 768
-    x = torch.randn(m, k, device=DEV).bfloat16()
-    w = (torch.randn(n, k, device=DEV) * 0.02).bfloat16()
-    bias = torch.randn(n, device=DEV)
-    pre = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
-    act = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
-    t = timeit(lambda: _C.gemm(x, w, pre, out2=act, bias=bias, epilogue=_C.EPI_GELU))
-    print(f"fc1 + bias + GELU (2 outputs): {t*1e3:.1f} us  {2.0*m*n*k/t/1e9:.0f} TF/s")
-    res = torch.randn(m, k, device=DEV)
-    h = torch.randn(m, n, device=DEV).bfloat16()
-    w2 = (torch.randn(k, n, device=DEV) * 0.02).bfloat16()
-    b2 = torch.randn(k, device=DEV)
-    t = timeit(lambda: _C.gemm(h, w2, res, bias=b2, residual=res))
-    print(f"fc2 + bias + fp32 residual in place: {t*1e3:.1f} us  {2.0*m*n*k/t/1e9:.0f} TF/s")
-    for bn in (64, 128, 256):
-        t = timeit(lambda: _C.gemm(x, w, pre, block_n=bn))
-        print(f"fc1 plain block_n={bn}: {t*1e3:.1f} us  {2.0*m*n*k/t/1e9:.0f} TF/s")
+        step = cnt * (t_f + t_d + t_w)
+        total += step
+        print(f"{name:14s} {m:6d} {n:5d} {k:5d} | {t_f*1e3:7.1f} {tf(t_f):6.0f} {tf(t_c):6.0f} | {t_d*1e3:7.1f} {tf(t_d):6.0f} {tf(t_dc):6.0f} | {t_w*1e3:7.1f} {tf(t_w):6.0f} {tf(t_wc):6.0f} | {step:6.2f}")
+    print(f"sum over the step's dominant GEMMs: {total:.2f} ms")
 
 
 if __name__ == "__main__":
