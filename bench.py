@@ -239,6 +239,7 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the timed host-buffer pass")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -323,7 +324,7 @@ def main() -> None:
         step_e2e()
     with ClockSampler(local_rank) as clocks:
         ms = timed(step_resident, args.steps)
-        ms_e2e = timed(step_e2e, args.steps)
+        ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
     final_loss = float(loss_host[0])
     n_vol = args.batch * world * args.steps
     value = n_vol / (ms / 1e3)

@@ -221,7 +221,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m_tile = tile / p.num_n_tiles;
       const long long row_base = (long long)m_tile * BM + q * 32;
       const int colw = n_tile * BN + cq * COLS_PER_WARP + c16 * 4;  // this lane's first column in chunk 0
-      if (has_res || has_aux) prefetch(row_base, colw);
+      if (has_res || has_aux) {
+        prefetch(row_base, colw);
+        // pull the NEXT tile's residual / GELU' operand rows of this warp into L2 (one 128-byte line per lane and step)
+        const int nitem = item + gridDim.x;
+        if (nitem < items) {
+          const int ntile = nitem / p.splits;
+          const long long nrow = (long long)(ntile / p.num_n_tiles) * BM + q * 32 + lane;
+          const int ncol = (ntile % p.num_n_tiles) * BN + cq * COLS_PER_WARP;
+          if (nrow < p.M && ncol < p.N) {
+            if (has_aux) {
+              const char* a = reinterpret_cast<const char*>(p.aux + nrow * p.ldaux + ncol);
+#pragma unroll
+              for (int o = 0; o < COLS_PER_WARP * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+            }
+            if (has_res) {
+              const char* a = reinterpret_cast<const char*>(p.residual + nrow * p.ldr + ncol);
+#pragma unroll
+              for (int o = 0; o < COLS_PER_WARP * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -378,35 +399,47 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
   p.num_m_tiles = (M + BM - 1) / BM;
 
   const int sms = cb_sm_count();
-  // pick the tile width that minimises (waves x per-tile time); ties go to the wider tile
-  int bn = block_n;
+  // Tile width and split-K factor from a small cost model (clocks per CTA): a k-block costs the slower of the MMA
+  // (135 clk per 128 x 256 x 16 instruction) and of its operand bytes at the per-SM share of the L2 -> SM bandwidth
+  // (~42 B/clk: B300_MICROARCH.md "LTS throughput cap" / 148 SMs), plus a fixed per-item prologue / epilogue.
+  auto plan = [&](int c, int want_splits, int& out_splits, int& out_kb_per_split) {
+    const long long tiles = (long long)p.num_m_tiles * ((N + c - 1) / c);
+    int sp = want_splits;
+    if (sp <= 0) {
+      sp = 1;
+      if (accumulate && tiles < sms) {  // wgrad-like: few tiles, long contraction -> split K
+        sp = (int)(sms / tiles);
+        const int max_splits = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
+        if (sp > max_splits) sp = max_splits;
+      }
+    }
+    if (sp > p.num_kb) sp = p.num_kb;
+    const int kbs = (p.num_kb + sp - 1) / sp;
+    sp = (p.num_kb + kbs - 1) / kbs;
+    out_splits = sp, out_kb_per_split = kbs;
+    const long long items = tiles * sp;
+    const long long waves = (items + sms - 1) / sms;
+    const double t_mma = 542.0 * c / 256.0;
+    const double t_load = (16384.0 + 128.0 * c) / 42.0;
+    const double t_kb = t_mma > t_load ? t_mma : t_load;
+    return (double)waves * (kbs * t_kb + 1500.0 + 6.0 * c);
+  };
+  int bn = block_n, splits = 1;
   if (bn != 64 && bn != 128 && bn != 256) {
     double best = 1e30;
     const int cands[3] = {256, 128, 64};
     for (int i = 0; i < 3; ++i) {
       const int c = cands[i];
       if (c > 64 && N <= c / 2) continue;
-      const long long t = (long long)p.num_m_tiles * ((N + c - 1) / c);
-      const long long waves = (t + sms - 1) / sms;
-      const double cost = (double)waves * (c + 24);  // +24: fixed per-tile overhead in "column" units
+      int sp, kbs;
+      const double cost = plan(c, split_k, sp, kbs);
       if (cost < best) best = cost, bn = c;
     }
   }
+  plan(bn, split_k, splits, p.kb_per_split);
   p.num_n_tiles = (N + bn - 1) / bn;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  int splits = split_k;
-  if (splits <= 0) {
-    splits = 1;
-    if (accumulate && tiles < sms) {  // wgrad-like: few tiles, long contraction -> split K
-      splits = sms / tiles;
-      const int max_splits = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
-      if (splits > max_splits) splits = max_splits;
-    }
-  }
-  if (splits > p.num_kb) splits = p.num_kb;
+  p.splits = splits;
   CB_CHECK_ARG(splits == 1 || accumulate, "gemm: split-K needs accumulate=1 (fp32 atomics into a zeroed/accumulated out)");
-  p.kb_per_split = (p.num_kb + splits - 1) / splits;
-  p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   CB_CHECK_ARG(p.splits == 1 || (bias == nullptr && residual == nullptr && epilogue == CB_EPI_NONE),
                "gemm: split-K supports no bias/residual/activation");
 
