@@ -21,7 +21,7 @@ namespace {
 
 constexpr int TQ = 128;       // query rows per tile (UMMA M)
 constexpr int TK = 128;       // keys per tile (UMMA N of S, K extent of P.V)
-constexpr int FWD_THREADS = 320;
+constexpr int FWD_THREADS = 384;  // 2 softmax warpgroups + 1 light warpgroup (TMA warp, MMA warp, 2 idle warps)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -106,7 +106,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp >= 8) {
+   // the light warpgroup hands registers to the softmax warpgroups (8 x 232 + 4 x 40 == 12 x 168)
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 8) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(q_full, n_tiles_q * C::TILE_BYTES);
@@ -124,7 +127,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+   } else if (warp == 9) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, false, false);
@@ -179,8 +182,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     __syncwarp();
+   }
   } else {
     // ------------------------------------------------ softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int t = warp >> 2;             // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;  // row inside the tile == TMEM lane
     if (t < n_tiles_q) {
@@ -188,33 +193,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint8_t* p_smem = smem + C::OFF_P + t * C::P_BYTES;
       float m_ref = -INFINITY;  // reference max (log2 domain) the accumulators are expressed against
       float l = 0.f;
+      const float sc = p.scale_log2;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&s_full[t], j & 1);
         tcgen05_fence_after();
-        float s[TK];
+        float s[TK];  // raw scores; scale and running max are folded into the exp2 argument below
+        {
+          uint32_t v[4][32];
 #pragma unroll
-        for (int c = 0; c < TK / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(lane_addr + t * TK + c * 32, v);
+          for (int c = 0; c < TK / 32; ++c) tmem_ld_32x32b_x32(lane_addr + t * TK + c * 32, v[c]);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
+          for (int c = 0; c < TK / 32; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[c][i]);
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
 
         const int valid = p.Nk - j * TK;  // keys of this tile that exist
-        float mx = -INFINITY;
+        if (valid < TK) {                 // ragged last tile only (CTA-uniform); kept out of line on purpose
+          asm volatile("" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < TK; ++i) {
-          if (i >= valid) s[i] = -INFINITY;
-          mx = fmaxf(mx, s[i]);
+          for (int i = 0; i < TK; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+          asm volatile("" ::: "memory");
         }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < TK; i += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], fmaxf(s[i + 2 * u], s[i + 2 * u + 1]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;  // scale > 0
         // lazy rescale: keep m_ref unless the row max ran away by more than 2^8
         const bool grow = mx > m_ref + RESCALE_THRESHOLD;
         const float m_new = grow ? mx : m_ref;
-        const float alpha = grow ? exp2f(m_ref - m_new) : 1.0f;  // exp2f(-inf) = 0 on the first tile
+        const float alpha = grow ? ex2_approx(m_ref - m_new) : 1.0f;  // 2^(-inf) = 0 on the first tile
         if (j > 0) {
           mbar_wait(&pv_done[t], (j - 1) & 1);  // P smem and O_t are quiescent
           tcgen05_fence_after();
@@ -233,20 +249,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         l *= alpha;
         m_ref = m_new;
-        float sum = 0.f;
+        const float neg_m = -m_ref;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int vcol = 0; vcol < TK / 8; ++vcol) {
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = exp2f(s[vcol * 8 + i] - m_ref);
-            sum += e[i];
-          }
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(s[vcol * 8 + i], sc, neg_m));
+          sum4[0] += e[0] + e[1], sum4[1] += e[2] + e[3], sum4[2] += e[4] + e[5], sum4[3] += e[6] + e[7];
           const uint4 pk = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
                                       pack_bf16(e[6], e[7]));
           *reinterpret_cast<uint4*>(p_smem + (vcol >> 3) * 16384 + sw128_vec_offset(r, vcol & 7)) = pk;
         }
-        l += sum;
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncwarp();
