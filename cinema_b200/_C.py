@@ -44,7 +44,7 @@ _SIGNATURES = {
                                  c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_void_p]),
     "cb_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong,
-                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_expand_token_index": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_dwconv_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -211,7 +211,8 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None,
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None,
-                  beta_act=None) -> None:
+                  beta_act=None, dxsum=None) -> None:
+    """dxsum (fp32 (D), optional) += column sums of the bf16-rounded dx: the bias gradient of the Linear fed by dx16."""
     m, d = x.shape
     dt = DT_BF16 if dy.dtype == torch.bfloat16 else DT_F32
     assert dy.dtype in (torch.bfloat16, torch.float32) and x.dtype == torch.float32
@@ -220,7 +221,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dga
                                   _row_major_2d(dres, "dres") if dres is not None else 0, m, d,
                                   _ptr(dx32), _row_major_2d(dx32, "dx32") if dx32 is not None else 0,
                                   _ptr(dx16), _row_major_2d(dx16, "dx16") if dx16 is not None else 0,
-                                  _ptr(dgamma), _ptr(dbeta), _ptr(beta_act), _stream()), "layernorm_bwd")
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), _ptr(beta_act), _stream()), "layernorm_bwd")
 
 
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:

@@ -98,11 +98,13 @@ def linear_gelu_fwd(x16: torch.Tensor, w: LinW) -> tuple[torch.Tensor, torch.Ten
 
 def linear_bwd(dy16: torch.Tensor, x16: torch.Tensor | None, w: LinW, *, need_dx: bool = True,
                gelu_aux: torch.Tensor | None = None, dx_dtype: torch.dtype = BF16,
-               dx_out: torch.Tensor | None = None) -> torch.Tensor | None:
-    """dW += dy^T x, db += colsum(dy), and dx = dy W (optionally * GELU'(gelu_aux), the input's pre-activation)."""
+               dx_out: torch.Tensor | None = None, bias_done: bool = False) -> torch.Tensor | None:
+    """dW += dy^T x, db += colsum(dy), and dx = dy W (optionally * GELU'(gelu_aux), the input's pre-activation).
+    ``bias_done``: the kernel that produced ``dy16`` already accumulated its column sums into ``w.gb``
+    (``ln_bwd(..., dxsum=w.gb)``)."""
     if w.gw is not None:
         _C.gemm(dy16, x16, w.gw, a_mn=True, b_mn=True, accumulate=True)
-    if w.gb is not None:
+    if w.gb is not None and not bias_done:
         _C.colsum(dy16, w.gb)
     if not need_dx:
         return None
@@ -148,16 +150,23 @@ def ln_fwd(x32: torch.Tensor, w: NormW, *, want16: bool = True, want32: bool = F
     return y16, y32, mean, rstd
 
 
+def fusable_bias(w: "LinW | None", d: int) -> torch.Tensor | None:
+    """Bias-gradient target of ``w`` if the LayerNorm backward can accumulate it (``dxsum``: TMA-staged path,
+    256 <= D <= 1024 with 16-byte bf16 rows)."""
+    return w.gb if (w is not None and w.gb is not None and d % 8 == 0 and 256 <= d <= 1024) else None
+
+
 def ln_bwd(dy: torch.Tensor, x32: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, w: NormW, *,
            dres: torch.Tensor | None = None, want16: bool = True, dx32: torch.Tensor | None = None,
-           beta_act: torch.Tensor | None = None):
-    """dx = LN'(dy) + dres -> (dx32, dx16).  ``dx32`` may alias ``dres`` (row-local read-then-write)."""
+           beta_act: torch.Tensor | None = None, dxsum: torch.Tensor | None = None):
+    """dx = LN'(dy) + dres -> (dx32, dx16).  ``dx32`` may alias ``dres`` (row-local read-then-write).
+    ``dxsum`` (D,) fp32 += column sums of dx16: the bias gradient of the Linear whose output gradient dx16 is."""
     m, d = x32.shape
     if dx32 is None:
         dx32 = torch.empty((m, d), dtype=F32, device=x32.device)
     dx16 = torch.empty((m, d), dtype=BF16, device=x32.device) if want16 else None
     _C.layernorm_bwd(dy, x32, mean, rstd, w.gamma, dres=dres, dx32=dx32, dx16=dx16, dgamma=w.gg, dbeta=w.gb,
-                     beta_act=beta_act)
+                     beta_act=beta_act, dxsum=dxsum)
     return dx32, dx16
 
 
@@ -262,20 +271,24 @@ def block_fwd(x: torch.Tensor, w: BlockW, b: int, kv: tuple[torch.Tensor, torch.
 
 
 def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
-              kv: tuple[torch.Tensor, torch.Tensor] | None, dkv: tuple[torch.Tensor, torch.Tensor] | None):
+              kv: tuple[torch.Tensor, torch.Tensor] | None, dkv: tuple[torch.Tensor, torch.Tensor] | None, *,
+              fc2_bias_done: bool = False, out_bias: torch.Tensor | None = None):
     """Backward of :func:`block_fwd`.  (dx32, dx16) is the gradient of the block output in fp32 and bf16.
     For cross-attention ``dkv`` are the (dk, dv) views this block's key / value gradients are written to.
+    ``fc2_bias_done``: the producer of ``dx16`` already accumulated ``fc2.bias``'s gradient; ``out_bias``: bias-gradient
+    buffer of the Linear that consumes the returned dx16 as its output gradient (fused into the last LayerNorm backward).
     Returns the (fp32, bf16) gradient of the block input; dx32 is updated in place."""
     x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act = saved
     m, d = x.shape
     n = m // b
     hd = d // w.n_heads
     # ---- MLP path
-    dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre)
+    dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done)
     dh2 = linear_bwd(dpre, h2, w.fc1)
-    dx32, dx16 = ln_bwd(dh2, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32)
+    proj_gb = fusable_bias(w.proj, d)
+    dx32, dx16 = ln_bwd(dh2, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32, dxsum=proj_gb)
     # ---- attention path
-    do2 = linear_bwd(dx16, o2, w.proj)
+    do2 = linear_bwd(dx16, o2, w.proj, bias_done=proj_gb is not None)
     do = do2.view(b, n, w.n_heads, hd)
     o = o2.view(b, n, w.n_heads, hd)
     if kv is None:
@@ -300,7 +313,7 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
         dq2 = torch.empty_like(qsave)
         attn_bwd(q, kv[0], kv[1], o, do, lse, dq2.view(b, n, w.n_heads, hd), dkv[0], dkv[1], w.scale)
         dh1 = linear_bwd(dq2, h1, w.q)
-    dx32, dx16 = ln_bwd(dh1, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32)
+    dx32, dx16 = ln_bwd(dh1, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32, dxsum=out_bias)
     return dx32, dx16
 
 

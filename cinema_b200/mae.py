@@ -238,9 +238,13 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
             dpf = engine.linear_bwd(dcur16, pf, wc, need_dx=tgt is not None)
             if tgt is not None:
                 _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
-    dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm)
-    for j in range(len(st.enc_w) - 1, -1, -1):
-        dx32, dx16 = engine.block_bwd(dx32, dx16, st.enc_w[j], b, st.enc_saved[j], None, None)
+    ew = st.enc_w
+    gb_of = lambda j: engine.fusable_bias(ew[j].fc2, d) if j >= 0 else None  # noqa: E731
+    dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm,
+                               dxsum=gb_of(len(ew) - 1))
+    for j in range(len(ew) - 1, -1, -1):
+        dx32, dx16 = engine.block_bwd(dx32, dx16, ew[j], b, st.enc_saved[j], None, None,
+                                      fc2_bias_done=gb_of(j) is not None, out_bias=gb_of(j - 1))
         st.enc_saved[j] = None
     dx0 = dx32.view(b, n, d)
     cls = model.encoder.cls_token
@@ -465,7 +469,10 @@ class _MAEFn(torch.autograd.Function):
             _C.scale_cast(diff, dpred, sc[i:i + 1])
             ddv = engine.linear_bwd(dpred.view(b * nm, -1), s["dvs"][i].view(b * nm, dd), s["heads"][i])
             _C.scatter_rows(ddv.view(b, nm, dd), engine.arange_idx(b, s["qoffs"][i], nm, dev), ddec)
-        dx32, dx16 = engine.ln_bwd(ddec.view(b * nq, dd), s["dec_last"], s["dmean"], s["drstd"], s["dec_norm"])
+        dec_w = s["dec_w"]
+        dgb_of = lambda j: engine.fusable_bias(dec_w[j].fc2, dd) if j >= 0 else None  # noqa: E731
+        dx32, dx16 = engine.ln_bwd(ddec.view(b * nq, dd), s["dec_last"], s["dmean"], s["drstd"], s["dec_norm"],
+                                   dxsum=dgb_of(len(dec_w) - 1))
         cross = s["cross"]
         dec_w, kvs, kv_all = s["dec_w"], s["kvs"], s["kv_all"]
         depth = len(dec_w)
@@ -478,7 +485,8 @@ class _MAEFn(torch.autograd.Function):
                 dkv_all = [torch.empty_like(t) for t in kv_all]
                 dkvs = [(t[:, :, 0], t[:, :, 1]) for t in dkv_all]
         for j in range(depth - 1, -1, -1):
-            dx32, dx16 = engine.block_bwd(dx32, dx16, dec_w[j], b, s["dec_saved"][j], kvs[j], dkvs[j] if cross else None)
+            dx32, dx16 = engine.block_bwd(dx32, dx16, dec_w[j], b, s["dec_saved"][j], kvs[j], dkvs[j] if cross else None,
+                                          fc2_bias_done=dgb_of(j) is not None, out_bias=dgb_of(j - 1))
             s["dec_saved"][j] = None
         dxq = dx32.view(b, nq, dd)
 

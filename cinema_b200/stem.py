@@ -105,18 +105,21 @@ def _block_fwd(x, w: ConvBlockW, geo: Geometry, f, save: bool):
     return x2, ((x, mean1, rstd1, h, h1, h2, x1, mean2, rstd2, g, pre, act) if save else None)
 
 
-def _block_bwd(dx32, dx16, w: ConvBlockW, geo: Geometry, f, saved):
+def _block_bwd(dx32, dx16, w: ConvBlockW, geo: Geometry, f, saved, fc2_bias_done: bool = False, out_bias=None):
+    """``fc2_bias_done`` / ``out_bias``: bias gradients fused into the producing LayerNorm backward (engine.block_bwd)."""
     x, mean1, rstd1, h, h1, h2, x1, mean2, rstd2, g, pre, act = saved
-    dpre = engine.linear_bwd(dx16, act, w.fc2, gelu_aux=pre)
+    c = x.shape[1]
+    dpre = engine.linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done)
     dg = engine.linear_bwd(dpre, g, w.fc1)
-    dx32, dx16 = engine.ln_bwd(dg, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32)
-    dh2 = engine.linear_bwd(dx16, h2, w.conv2)
+    conv2_gb = engine.fusable_bias(w.conv2, c)
+    dx32, dx16 = engine.ln_bwd(dg, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32, dxsum=conv2_gb)
+    dh2 = engine.linear_bwd(dx16, h2, w.conv2, bias_done=conv2_gb is not None)
     if w.dw.gw is not None:
         _C.dwconv_tokens_wgrad(h1, dh2, w.dw.gw, w.dw.gb, geo.mask, geo.slot, geo.keep, geo.grid_tok, f)
     dh1 = torch.empty_like(dh2)
     _C.dwconv_tokens(dh2, dh1, w.dw.w16, None, geo.mask, geo.slot, geo.keep, geo.grid_tok, f, transpose=True)
     dh = engine.linear_bwd(dh1, h, w.conv1)
-    return engine.ln_bwd(dh, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32)
+    return engine.ln_bwd(dh, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32, dxsum=out_bias)
 
 
 def stem_fwd(levels: list[LevelW], image32: torch.Tensor, geo: Geometry, save: bool):
@@ -157,8 +160,11 @@ def stem_bwd(levels: list[LevelW], geo: Geometry, saved, dlevels: list[torch.Ten
         dx32 = dlevels[li]
         dx16 = torch.empty(dx32.shape, dtype=BF16, device=dx32.device)
         _C.cast_bf16(dx32, dx16)
+        gb_of = lambda bi: engine.fusable_bias(lw.blocks[bi].fc2, lw.chans) if bi >= 0 else None  # noqa: E731,B023
         for bi in range(len(lw.blocks) - 1, -1, -1):
-            dx32, dx16 = _block_bwd(dx32, dx16, lw.blocks[bi], geo, lw.f, bsaved[bi])
+            done = bi < len(lw.blocks) - 1 and gb_of(bi) is not None  # the level's entry dx16 is a plain cast
+            dx32, dx16 = _block_bwd(dx32, dx16, lw.blocks[bi], geo, lw.f, bsaved[bi], fc2_bias_done=done,
+                                    out_bias=gb_of(bi - 1))
             bsaved[bi] = None
         # LayerNorm + GELU backward (dy of the patch conv), then the conv's wgrad / dgrad
         _, dy16 = engine.ln_bwd(dx32, y, mean, rstd, lw.norm, dx32=dx32, beta_act=lw.norm.beta)

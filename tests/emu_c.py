@@ -97,7 +97,8 @@ def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None,
         rstd.copy_(r.squeeze(-1))
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None, beta_act=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dgamma=None, dbeta=None, beta_act=None,
+                  dxsum=None):
     d = dy.float()
     xh = (x - mean[:, None]) * rstd[:, None]
     if beta_act is not None:
@@ -116,6 +117,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dx32=None, dx16=None, dga
         dx32.copy_(o)
     if dx16 is not None:
         dx16.copy_(o.to(BF16))
+    if dxsum is not None:
+        dxsum.add_(o.to(BF16).float().sum(0))
 
 
 def cast_bf16(src, dst):

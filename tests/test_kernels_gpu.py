@@ -181,6 +181,15 @@ def test_layernorm_fwd_bwd(m, d):
     xr.grad = None
     torch.nn.functional.layer_norm(xr, (d,), gamma, beta, 1e-5).backward(dy16.float())
     torch.testing.assert_close(dx32, xr.grad, rtol=1e-4, atol=1e-4)
+    if d % 8 == 0 and 256 <= d <= 1024:
+        # in-place residual (dx32 aliases dres) with the fused column sums of the bf16 output (bias gradient of the
+        # consuming Linear): must equal a separate colsum over dx16
+        acc = dres.clone()
+        dxsum = torch.zeros(d, device=DEV)
+        _C.layernorm_bwd(dy16, x, mean, rstd, gamma, dres=acc, dx32=acc, dx16=dx16, dxsum=dxsum)
+        torch.testing.assert_close(acc, xr.grad + dres, rtol=1e-4, atol=1e-4)
+        assert torch.equal(dx16, acc.to(torch.bfloat16))
+        torch.testing.assert_close(dxsum, dx16.float().sum(0), rtol=1e-4, atol=2e-3)
 
 
 # ----------------------------------------------------------------------------- data movement

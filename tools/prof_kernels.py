@@ -107,13 +107,16 @@ def main():
         return
     for name, fn, by, fl in kernels:
         ts = []
-        for _ in range(10):
+        reps = 4
+        for _ in range(6):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(1_500_000)  # let the host run ahead: launches are queued, not timed
             e0.record()
-            fn()
+            for _ in range(reps):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / reps)
         t = sorted(ts)[len(ts) // 2]
         extra = f"{by / t / 1e6:8.0f} GB/s" if by else ""
         extra += f"{fl / t / 1e9:8.0f} TF/s" if fl else ""
