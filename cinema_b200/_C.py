@@ -193,9 +193,19 @@ def attention_fwd(q, k, v, o, lse, scale: float) -> None:
                                   d, float(scale), _stream()), "attention_fwd")
 
 
+def attention_bwd_workspace(b: int, h: int, nq: int, d: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    """(delta, dq_acc) scratch of cb_attention_bwd: delta holds two (B*H, NqP) fp32 vectors (NqP = Nq rounded up to
+    128), dq_acc the fp32 dQ accumulator (B, H, Nq, d)."""
+    nqp = (nq + 127) // 128 * 128
+    return (torch.empty((2, b * h, nqp), dtype=torch.float32, device=device),
+            torch.empty((b, h, nq, d), dtype=torch.float32, device=device))
+
+
 def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale: float) -> None:
     b, nq, h, d = q.shape
     nk = k.shape[1]
+    assert delta.dtype == torch.float32 and delta.numel() >= 2 * b * h * ((nq + 127) // 128 * 128), "delta workspace too small"
+    assert dq_acc.dtype == torch.float32 and dq_acc.numel() >= b * h * nq * d
     _check(lib().cb_attention_bwd(*_bnh(q, "q"), *_bnh(k, "k"), *_bnh(v, "v"), *_bnh(o, "o"), *_bnh(do, "do"),
                                   _ptr(lse), *_bnh(dq, "dq"), *_bnh(dk, "dk"), *_bnh(dv, "dv"), _ptr(delta),
                                   _ptr(dq_acc), b, h, nq, nk, d, float(scale), _stream()), "attention_bwd")

@@ -49,6 +49,14 @@ struct FwdCfg {
   static constexpr int TMEM_O = 256;                          // column of O0; O1 at +D
 };
 
+// 1-D bulk copy global -> shared, completion (bytes) on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // element (row, col) of a K-major 128B-swizzled [128 x 64] bf16 chunk -> byte offset of its 16-byte vector
 __device__ __forceinline__ uint32_t sw128_vec_offset(int row, int vec /*0..7*/) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((vec ^ (row & 7)) << 4));
@@ -368,11 +376,12 @@ extern "C" int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, l
 // ============================================================================================
 namespace {
 
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 384;  // 2 compute warpgroups + 1 light warpgroup (TMA warp, MMA warp, 2 idle warps)
 
 struct AttnBwdArgs {
-  const float* lse;
-  const float* delta;
+  const float* nl2;  // [B*H, NqP]  -lse * log2(e)      (attn_delta_kernel; NqP = Nq rounded up to 128, pads = -inf)
+  const float* dsc;  // [B*H, NqP]  delta * scale       (pads = 0)
+  int NqP;
   float* dq_acc;  // [B, H, Nq, D] fp32, pre-zeroed
   bf16* dk;
   long long dk_sb, dk_sn, dk_sh;
@@ -452,7 +461,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp >= 8) {
+   // the light warpgroup hands registers to the compute warpgroups (8 x 232 + 4 x 40 == 12 x 168)
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 8) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * C::TILE_BYTES);
@@ -461,9 +473,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int i = 0; i < n_q; ++i) {
         const int s = i & 1;
         mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qdo_full[s], 2 * C::TILE_BYTES);
+        mbar_expect_tx(&qdo_full[s], 2 * C::TILE_BYTES + 1024);
         tma_load_4d(smem + C::OFF_Q + s * C::TILE_BYTES, &tm_q, &qdo_full[s], 0, h, i * 128, b);
         tma_load_4d(smem + C::OFF_DO + s * C::TILE_BYTES, &tm_do, &qdo_full[s], 0, h, i * 128, b);
+        const long long voff = ((long long)b * p.H + h) * p.NqP + i * 128;  // per-query vectors of this tile
+        bulk_load_1d(vec + s * 256, p.nl2 + voff, 512, &qdo_full[s]);
+        bulk_load_1d(vec + s * 256 + 128, p.dsc + voff, 512, &qdo_full[s]);
       }
     }
     __syncwarp();
@@ -532,16 +547,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     __syncwarp();
+   }
   } else {
     // ------------------------------------------------ two compute warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int wg = warp >> 2;                 // query-column half handled by this warpgroup
     const int r = (warp & 3) * 32 + lane;     // key row inside the tile == TMEM lane
-    const int tid = threadIdx.x;              // 0..255
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    uint8_t* p_smem = smem + C::OFF_P + wg * 16384;
-    uint8_t* ds_smem = smem + C::OFF_DS + wg * 16384;
-    const float* lse_g = p.lse + ((long long)b * p.H + h) * p.Nq;
-    const float* delta_g = p.delta + ((long long)b * p.H + h) * p.Nq;
     float* dq_g = p.dq_acc + ((long long)b * p.H + h) * p.Nq * D;
 
     auto drain_dq = [&](int i) {  // dQ tile i: lanes = query rows, this warpgroup takes D/2 columns
@@ -564,56 +576,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (lane == 0) mbar_arrive(dq_free);
     };
 
-    // prefetch of the per-query vectors of tile 0 (thread tid < 128 owns query column tid)
-    float lse_next = INFINITY, delta_next = 0.f;
-    if (tid < 128 && tid < p.Nq) lse_next = lse_g[tid] * LOG2E, delta_next = delta_g[tid];
-
+    const uint32_t p_s32 = smem_u32(smem + C::OFF_P + wg * 16384);
+    const uint32_t ds_s32 = smem_u32(smem + C::OFF_DS + wg * 16384);
     for (int i = 0; i < n_q; ++i) {
-      float* lse_s = vec + (i & 1) * 256;
-      float* delta_s = lse_s + 128;
-      if (tid < 128) {
-        lse_s[tid] = lse_next, delta_s[tid] = delta_next;
-        const int qn = (i + 1) * 128 + tid;
-        lse_next = INFINITY, delta_next = 0.f;
-        if (i + 1 < n_q && qn < p.Nq) lse_next = lse_g[qn] * LOG2E, delta_next = delta_g[qn];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-
+      // -lse*log2e and delta*scale of this tile's 128 queries arrive with the Q / dO stage (bulk copies)
+      const float4* nl4 = reinterpret_cast<const float4*>(vec + (i & 1) * 256) + wg * 16;
+      const float4* ds4 = nl4 + 32;
       float s[64], dp[64];
       mbar_wait(s_full, i & 1);
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_addr + C::TM_S + wg * 64 + c * 32, v);
+      {
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(lane_addr + C::TM_S + wg * 64, v[0]);
+        tmem_ld_32x32b_x32(lane_addr + C::TM_S + wg * 64 + 32, v[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) s[c * 32 + k] = __uint_as_float(v[k]);
+        for (int k = 0; k < 64; ++k) s[k] = __uint_as_float(v[k >> 5][k & 31]);
       }
       mbar_wait(dp_full, i & 1);
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_addr + C::TM_DP + wg * 64 + c * 32, v);
+      {
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(lane_addr + C::TM_DP + wg * 64, v[0]);
+        tmem_ld_32x32b_x32(lane_addr + C::TM_DP + wg * 64 + 32, v[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) dp[c * 32 + k] = __uint_as_float(v[k]);
+        for (int k = 0; k < 64; ++k) dp[k] = __uint_as_float(v[k >> 5][k & 31]);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);
+      mbar_wait(&qdo_full[i & 1], (i >> 1) & 1);  // the vectors travelled with this stage
 
       uint32_t pk[32], dsk[32];  // packed bf16 P^T and dS^T of this row half
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int q_a = wg * 64 + 2 * c;
-        const float p0 = exp2f(fmaf(s[2 * c], p.scale_log2, -lse_s[q_a]));
-        const float p1 = exp2f(fmaf(s[2 * c + 1], p.scale_log2, -lse_s[q_a + 1]));
-        const float d0 = p0 * (dp[2 * c] - delta_s[q_a]) * p.scale;
-        const float d1 = p1 * (dp[2 * c + 1] - delta_s[q_a + 1]) * p.scale;
-        pk[c] = pack_bf16(p0, p1);
-        dsk[c] = pack_bf16(d0, d1);
+      for (int g = 0; g < 16; ++g) {
+        const float4 nl = nl4[g], dsv = ds4[g];
+        const float p0 = ex2_approx(fmaf(s[4 * g + 0], p.scale_log2, nl.x));
+        const float p1 = ex2_approx(fmaf(s[4 * g + 1], p.scale_log2, nl.y));
+        const float p2 = ex2_approx(fmaf(s[4 * g + 2], p.scale_log2, nl.z));
+        const float p3 = ex2_approx(fmaf(s[4 * g + 3], p.scale_log2, nl.w));
+        pk[2 * g] = pack_bf16(p0, p1);
+        pk[2 * g + 1] = pack_bf16(p2, p3);
+        dsk[2 * g] = pack_bf16(p0 * fmaf(dp[4 * g + 0], p.scale, -dsv.x), p1 * fmaf(dp[4 * g + 1], p.scale, -dsv.y));
+        dsk[2 * g + 1] = pack_bf16(p2 * fmaf(dp[4 * g + 2], p.scale, -dsv.z), p3 * fmaf(dp[4 * g + 3], p.scale, -dsv.w));
       }
       if (i > 0) {
         mbar_wait(mma2_done, (i - 1) & 1);  // P / dS smem reusable, dQ_{i-1} complete
@@ -623,9 +629,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int vcol = 0; vcol < 8; ++vcol) {
         const uint32_t off = sw128_vec_offset(r, vcol);
-        *reinterpret_cast<uint4*>(p_smem + off) = make_uint4(pk[4 * vcol], pk[4 * vcol + 1], pk[4 * vcol + 2], pk[4 * vcol + 3]);
-        *reinterpret_cast<uint4*>(ds_smem + off) =
-            make_uint4(dsk[4 * vcol], dsk[4 * vcol + 1], dsk[4 * vcol + 2], dsk[4 * vcol + 3]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_s32 + off), "r"(pk[4 * vcol]), "r"(pk[4 * vcol + 1]),
+                     "r"(pk[4 * vcol + 2]), "r"(pk[4 * vcol + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s32 + off), "r"(dsk[4 * vcol]),
+                     "r"(dsk[4 * vcol + 1]), "r"(dsk[4 * vcol + 2]), "r"(dsk[4 * vcol + 3])
+                     : "memory");
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
@@ -671,20 +680,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
-// delta[b,h,q] = sum_d O[b,q,h,d] * dO[b,q,h,d]; 8 lanes per (b,q,h) row, 16-byte loads
+// Per-query vectors of the backward, 8 lanes per (b, h, q) row, 16-byte loads:
+//   dsc[bh, q] = scale * sum_d O[b,q,h,d] * dO[b,q,h,d]      nl2[bh, q] = -lse[b,h,q] * log2(e)
+// rows are padded to NqP = 128 * ceil(Nq / 128) entries (nl2 = -inf -> P = 0, dsc = 0) so that the main kernel can
+// fetch whole 128-query vectors with one bulk copy each.
 template <int D>
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sn, long long o_sh,
                                   const bf16* __restrict__ d_o, long long do_sb, long long do_sn, long long do_sh,
-                                  float* __restrict__ delta, int B, int H, int Nq) {
+                                  const float* __restrict__ lse, float* __restrict__ nl2, float* __restrict__ dsc, int B,
+                                  int H, int Nq, int NqP, float scale) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long row = gid >> 3;
+  const long long row = gid >> 3;  // over B * H * NqP
   const int sub = (int)(gid & 7);
-  const long long total = (long long)B * H * Nq;
+  const long long total = (long long)B * H * NqP;
   float acc = 0.f;
-  if (row < total) {
-    const int q = (int)(row % Nq);
-    const int h = (int)((row / Nq) % H);
-    const int b = (int)(row / ((long long)Nq * H));
+  const int q = (int)(row % NqP);
+  const long long bh = row / NqP;
+  const bool live = row < total && q < Nq;
+  if (live) {
+    const int h = (int)(bh % H);
+    const int b = (int)(bh / H);
     const bf16* op = o + b * o_sb + (long long)q * o_sn + (long long)h * o_sh;
     const bf16* dp = d_o + b * do_sb + (long long)q * do_sn + (long long)h * do_sh;
     for (int c = sub * 8; c < D; c += 64) {
@@ -701,7 +716,10 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, lo
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (row < total && sub == 0) delta[row] = acc;
+  if (row < total && sub == 0) {
+    dsc[row] = live ? acc * scale : 0.f;
+    nl2[row] = live ? -lse[bh * Nq + q] * LOG2E : -INFINITY;
+  }
 }
 
 // dq[b,q,h,:] = bf16(dq_acc[b,h,q,:])
@@ -725,12 +743,14 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __re
 template <int D>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                const AttnBwdArgs& a, const bf16* o, long long o_sb, long long o_sn, long long o_sh, const bf16* d_o,
-               long long do_sb, long long do_sn, long long do_sh, float* delta, bf16* dq, long long dq_sb,
+               long long do_sb, long long do_sn, long long do_sh, const float* lse, bf16* dq, long long dq_sb,
                long long dq_sn, long long dq_sh, cudaStream_t stream) {
   using C = BwdCfg<D>;
   const long long rows = (long long)a.B * a.H * a.Nq;
-  attn_delta_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, stream>>>(o, o_sb, o_sn, o_sh, d_o, do_sb, do_sn,
-                                                                             do_sh, delta, a.B, a.H, a.Nq);
+  const long long rows_p = (long long)a.B * a.H * a.NqP;
+  attn_delta_kernel<D><<<(unsigned)((rows_p * 8 + 255) / 256), 256, 0, stream>>>(
+      o, o_sb, o_sn, o_sh, d_o, do_sb, do_sn, do_sh, lse, const_cast<float*>(a.nl2), const_cast<float*>(a.dsc), a.B, a.H, a.Nq,
+      a.NqP, a.scale);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)rows * D * sizeof(float), stream));
   auto kern = attn_bwd_kernel<D>;
@@ -768,14 +788,15 @@ extern "C" int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, l
   if (int rc = make_qkv_tmap(&tv, v, v_sb, v_sn, v_sh, B, H, Nk, head_dim, 128)) return rc;
   if (int rc = make_qkv_tmap(&tdo, d_o, do_sb, do_sn, do_sh, B, H, Nq, head_dim, 128)) return rc;
   AttnBwdArgs a;
-  a.lse = lse, a.delta = delta, a.dq_acc = dq_acc;
+  a.NqP = (Nq + 127) / 128 * 128;
+  a.nl2 = delta, a.dsc = delta + (long long)B * H * a.NqP, a.dq_acc = dq_acc;
   a.dk = (bf16*)dk, a.dk_sb = dk_sb, a.dk_sn = dk_sn, a.dk_sh = dk_sh;
   a.dv = (bf16*)dv, a.dv_sb = dv_sb, a.dv_sn = dv_sn, a.dv_sh = dv_sh;
   a.B = B, a.H = H, a.Nq = Nq, a.Nk = Nk, a.scale = scale, a.scale_log2 = scale * LOG2E;
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 64)
     return launch_bwd<64>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh,
-                          delta, (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
-  return launch_bwd<32>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh, delta,
+                          lse, (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
+  return launch_bwd<32>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh, lse,
                         (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
 }

@@ -191,8 +191,7 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
 
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, scale: float) -> None:
     b, nq, h, d = q.shape
-    delta = torch.empty((b, h, nq), dtype=F32, device=q.device)
-    dq_acc = torch.empty((b, h, nq, d), dtype=F32, device=q.device)
+    delta, dq_acc = _C.attention_bwd_workspace(b, h, nq, d, q.device)
     _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale)
 
 

@@ -64,8 +64,9 @@ int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, long long q_
                      long long k_sn, long long k_sh, const void* v, long long v_sb, long long v_sn, long long v_sh,
                      void* o, long long o_sb, long long o_sn, long long o_sh, float* lse, int B, int H, int Nq, int Nk,
                      int head_dim, float scale, void* stream);
-/* dQ, dK, dV (bf16, same addressing scheme).  delta[b,h,q] (fp32 scratch, B*H*Nq) and
- * dq_acc (fp32 scratch, B*H*Nq*head_dim) are caller-provided workspaces. */
+/* dQ, dK, dV (bf16, same addressing scheme).  Caller-provided workspaces: delta (fp32 scratch, 2 * B*H*NqP floats with
+ * NqP = Nq rounded up to a multiple of 128: the per-query vectors -lse*log2(e) and scale*rowsum(O o dO), padded so
+ * that the kernel fetches them with 512-byte bulk copies) and dq_acc (fp32 scratch, B*H*Nq*head_dim). */
 int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, long long q_sh, const void* k, long long k_sb,
                      long long k_sn, long long k_sh, const void* v, long long v_sb, long long v_sn, long long v_sh,
                      const void* o, long long o_sb, long long o_sn, long long o_sh, const void* d_o, long long do_sb,

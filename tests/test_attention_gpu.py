@@ -88,8 +88,7 @@ def test_attention_backward(b, h, nq, nk, d, fused):
     do = torch.randn(b, nq, h, d, device=DEV, generator=g).to(torch.bfloat16)
     dq = torch.empty(b, nq, h, d, device=DEV, dtype=torch.bfloat16)
     dkv = torch.empty(b, nk, 2, h, d, device=DEV, dtype=torch.bfloat16)
-    delta = torch.empty(b, h, nq, device=DEV)
-    dq_acc = torch.empty(b, h, nq, d, device=DEV)
+    delta, dq_acc = _C.attention_bwd_workspace(b, h, nq, d, DEV)
     _C.attention_bwd(q, k, v, o, do, lse, dq, dkv[:, :, 0], dkv[:, :, 1], delta, dq_acc, scale)
 
     qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))

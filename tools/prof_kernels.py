@@ -45,8 +45,7 @@ def build(only):
             K.append((f"attn_fwd {tag} d{d}", lambda q=q, k=k, v=v, o=o, lse=lse, sc=sc: _C.attention_fwd(q, k, v, o, lse, sc), 0, fl))
             do = rn(B, nq, h, d, dtype=BF)
             dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-            delta = torch.empty(B, h, nq, device=DEV)
-            dqa = torch.empty(B, h, nq, d, device=DEV)
+            delta, dqa = _C.attention_bwd_workspace(B, h, nq, d, DEV)
             _C.attention_fwd(q, k, v, o, lse, sc)
             K.append((f"attn_bwd {tag} d{d}", lambda q=q, k=k, v=v, o=o, do=do, lse=lse, dq=dq, dk=dk, dv=dv, delta=delta, dqa=dqa, sc=sc: _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dqa, sc), 0, 2 * fl))
     if "gemm" in only:
