@@ -18,6 +18,9 @@
 #include "../../include/cinema_b200.h"
 #include "common.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace {
 
 constexpr int BM = 128;
@@ -42,12 +45,15 @@ struct GemmArgs {
   float alpha;
 };
 
-template <int BN>
+// CTAS == 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2; each
+// CTA stages its own 128 rows of A and HALF of the B tile, so every SM receives 16 + BN/16 KB per k-block instead of
+// 16 + BN/8 KB -- the L2 -> SM bandwidth is what bounds the single-CTA kernel (~1000 TFLOP/s with 128 x 256 tiles).
+template <int BN, int CTAS = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN / CTAS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
   static constexpr int STAGING_BYTES = EPI_WARPS * 2048;  // per-warp 32 x 16 fp32 epilogue transposition tile
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -57,10 +63,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  constexpr bool PAIR = CTAS == 2;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs of the pair)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
@@ -84,51 +92,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], EPI_WARPS);
+        mbar_init(&tempty_bar[s], EPI_WARPS * CTAS);  // pair: the leader collects the epilogue warps of both CTAs
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;  // pair: num_m_tiles counts 256-row tiles
   const int items = tiles * p.splits;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-scheduler slot of this CTA (pair)
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = BM * CTAS;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = worker; item < items; item += n_workers) {
         const int split = item % p.splits;
         const int tile = item / p.splits;
         const int n_tile = tile % p.num_n_tiles;
         const int m_tile = tile / p.num_n_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const int m0 = m_tile * TILE_M + (int)cta_rank * BM;          // this CTA's rows of A
+        const int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);     // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          // pair: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+          if (!PAIR || cta_rank == 0) mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES * CTAS);
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_tile * BM);
+            tma_load_2d_g<CTAS>(sa, &tma_a, &full_bar[stage], kb * BK, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_tile * BM + j * 64, kb * BK);
+              tma_load_2d_g<CTAS>(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_tile * BN);
+            tma_load_2d_g<CTAS>(sb, &tma_b, &full_bar[stage], kb * BK, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n_tile * BN + j * 64, kb * BK);
+            for (int j = 0; j < BN / CTAS / 64; ++j)
+              tma_load_2d_g<CTAS>(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -140,13 +156,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int item = worker; item < items; item += n_workers) {
         const int split = item % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -164,15 +180,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                      : umma_smem_desc(a_base + k * 32, 0, 1024, UMMA_SW128);
             const uint64_t db = B_MN ? umma_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_SW128)
                                      : umma_smem_desc(b_base + k * 32, 0, 1024, UMMA_SW128);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss_g<CTAS>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          umma_commit_g<CTAS>(&empty_bar[stage]);  // smem slot (of both CTAs) reusable once these MMAs retire
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit_g<CTAS>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -198,44 +214,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int c16 = lane & 3;   // 16-byte column (4 fp32) inside the 16-column chunk
     const bool has_res = p.residual != nullptr;
     const bool has_aux = p.epi == CB_EPI_GELU_BWD;
+    const bool has_bias = p.bias != nullptr;
+    const bool has_out2 = p.out2 != nullptr;
+    // all epilogue addressing is base pointer + 32-bit element offset (host checks M * ld < 2^31): one IMAD.WIDE per
+    // access instead of 64-bit row arithmetic, which used to be half of the epilogue's instructions
+    const int so8 = (int)(8 * p.ldo), s28 = (int)(8 * p.ldo2), sr8 = (int)(8 * p.ldr), sa8 = (int)(8 * p.ldaux);
+    float* const out32 = reinterpret_cast<float*>(p.out);
+    bf16* const out16 = reinterpret_cast<bf16*>(p.out);
     int acc = 0;
     uint32_t acc_phase = 0;
     float4 pre_res[4];
     uint2 pre_aux[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) pre_res[i] = make_float4(0.f, 0.f, 0.f, 0.f), pre_aux[i] = make_uint2(0u, 0u);
-    auto prefetch = [&](long long row_base, int col) {
-      if (col >= p.N) return;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long row = row_base + i * 8 + sub;
-        if (row < p.M) {
-          if (has_res) pre_res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
-          if (has_aux) pre_aux[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col));
-        }
-      }
-    };
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+
+    // one 128 x BN accumulator tile; MODE is a compile-time constant so that each epilogue flavour gets its own loop
+    auto run_tile = [&](auto mode_c, int item) {
+      constexpr int MODE = decltype(mode_c)::value;  // 0 bf16 out, 1 GELU, 2 GELU', 3 fp32 out, 4 fp32 atomic add
       const int tile = item / p.splits;
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
-      const long long row_base = (long long)m_tile * BM + q * 32;
-      const int colw = n_tile * BN + cq * COLS_PER_WARP + c16 * 4;  // this lane's first column in chunk 0
-      if (has_res || has_aux) {
-        prefetch(row_base, colw);
+      const int r0 = m_tile * TILE_M + (int)cta_rank * BM + q * 32 + sub;  // this lane's first row (i = 0)
+      const int colw = n_tile * BN + cq * COLS_PER_WARP + c16 * 4;         // this lane's first column in chunk 0
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vmask |= (r0 + 8 * i < p.M ? 1u : 0u) << i;
+      const int oo = (int)((long long)r0 * p.ldo) + colw;
+      const int o2 = (int)((long long)r0 * p.ldo2) + colw;
+      const int ro = (int)((long long)r0 * p.ldr) + colw;
+      const int ao = (int)((long long)r0 * p.ldaux) + colw;
+      auto prefetch = [&](int c) {  // residual / GELU' operands of chunk c into registers
+        if (colw + c * 16 >= p.N) return;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((vmask >> i) & 1u) {
+            if ((MODE == 0 || MODE == 3) && has_res)
+              pre_res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (ro + i * sr8 + c * 16)));
+            if (MODE == 2) pre_aux[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + (ao + i * sa8 + c * 16)));
+          }
+        }
+      };
+      if (MODE == 2 || ((MODE == 0 || MODE == 3) && has_res)) {
+        prefetch(0);
         // pull the NEXT tile's residual / GELU' operand rows of this warp into L2 (one 128-byte line per lane and step)
-        const int nitem = item + gridDim.x;
+        const int nitem = item + n_workers;
         if (nitem < items) {
           const int ntile = nitem / p.splits;
-          const long long nrow = (long long)(ntile / p.num_n_tiles) * BM + q * 32 + lane;
+          const long long nrow = (long long)(ntile / p.num_n_tiles) * TILE_M + (long long)cta_rank * BM + q * 32 + lane;
           const int ncol = (ntile % p.num_n_tiles) * BN + cq * COLS_PER_WARP;
           if (nrow < p.M && ncol < p.N) {
-            if (has_aux) {
+            if (MODE == 2) {
               const char* a = reinterpret_cast<const char*>(p.aux + nrow * p.ldaux + ncol);
 #pragma unroll
               for (int o = 0; o < COLS_PER_WARP * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
-            }
-            if (has_res) {
+            } else {
               const char* a = reinterpret_cast<const char*>(p.residual + nrow * p.ldr + ncol);
 #pragma unroll
               for (int o = 0; o < COLS_PER_WARP * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
@@ -251,8 +283,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t r[16];
         tmem_ld_32x32b_x16(taddr, r);
         tmem_ld_wait();
-        long long rb = row_base;
-        asm volatile("" : "+l"(rb));  // keep the per-row address arithmetic inside the chunk loop (register pressure)
         const int col = colw + c * 16;
         const bool col_ok = col < p.N;  // N is a multiple of 8
 #pragma unroll
@@ -262,7 +292,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                        : "memory");
         __syncwarp();
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         float x[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -276,64 +306,78 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint2 aux[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) res[i] = pre_res[i], aux[i] = pre_aux[i];
-        if ((has_res || has_aux) && c + 1 < CHUNKS) prefetch(rb, col + 16);
+        if ((MODE == 2 || ((MODE == 0 || MODE == 3) && has_res)) && c + 1 < CHUNKS) prefetch(c + 1);
+        if (!col_ok) continue;  // warp-uniform per 16-byte column group only when N % 16 != 0; harmless otherwise
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const long long row = rb + i * 8 + sub;
-          if (row >= p.M || !col_ok) continue;
+          if (!((vmask >> i) & 1u)) continue;
           float* v = x[i];
           v[0] = fmaf(v[0], p.alpha, bias4.x), v[1] = fmaf(v[1], p.alpha, bias4.y);
           v[2] = fmaf(v[2], p.alpha, bias4.z), v[3] = fmaf(v[3], p.alpha, bias4.w);
-          if (p.epi == CB_EPI_GELU) {
+          const int eo = oo + i * so8 + c * 16;
+          if constexpr (MODE == 1) {
             // pre-activation is rounded to bf16 first (what autocast feeds nn.GELU), saved for backward
             const uint2 pre = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-            if (p.out != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) = pre;
+            if (p.out != nullptr) *reinterpret_cast<uint2*>(out16 + eo) = pre;
             const float2 p0 = unpack_bf16(pre.x), p1 = unpack_bf16(pre.y);
-            *reinterpret_cast<uint2*>(p.out2 + row * p.ldo2 + col) =
+            *reinterpret_cast<uint2*>(p.out2 + (o2 + i * s28 + c * 16)) =
                 make_uint2(pack_bf16(gelu_fast(p0.x), gelu_fast(p0.y)), pack_bf16(gelu_fast(p1.x), gelu_fast(p1.y)));
-            continue;
-          }
-          if (has_aux) {
+          } else if constexpr (MODE == 2) {
             const float2 a0 = unpack_bf16(aux[i].x), a1 = unpack_bf16(aux[i].y);
             v[0] *= gelu_grad_fast(a0.x), v[1] *= gelu_grad_fast(a0.y);
             v[2] *= gelu_grad_fast(a1.x), v[3] *= gelu_grad_fast(a1.y);
-          }
-          if (has_res) v[0] += res[i].x, v[1] += res[i].y, v[2] += res[i].z, v[3] += res[i].w;
-          if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-            if (p.atomic_add)
-              red_add_v4(o, v[0], v[1], v[2], v[3]);
-            else
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint2*>(out16 + eo) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+          } else if constexpr (MODE == 4) {
+            red_add_v4(out32 + eo, v[0], v[1], v[2], v[3]);
           } else {
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + row * p.ldo + col) =
-                make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            if (has_res) v[0] += res[i].x, v[1] += res[i].y, v[2] += res[i].z, v[3] += res[i].w;
+            const uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            if constexpr (MODE == 3) {
+              *reinterpret_cast<float4*>(out32 + eo) = make_float4(v[0], v[1], v[2], v[3]);
+              if (has_out2) *reinterpret_cast<uint2*>(p.out2 + (o2 + i * s28 + c * 16)) = pk;  // bf16 shadow
+            } else {
+              *reinterpret_cast<uint2*>(out16 + eo) = pk;
+              if (has_out2) *reinterpret_cast<uint2*>(p.out2 + (o2 + i * s28 + c * 16)) = pk;
+            }
           }
-          if (p.out2 != nullptr)  // optional bf16 shadow of an fp32 result
-            *reinterpret_cast<uint2*>(p.out2 + row * p.ldo2 + col) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's barrier gates the MMAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
+      }
+    };
+    const int mode = p.epi == CB_EPI_GELU ? 1 : (has_aux ? 2 : (p.out_fp32 ? (p.atomic_add ? 4 : 3) : 0));
+    for (int item = worker; item < items; item += n_workers) {
+      switch (mode) {
+        case 0: run_tile(std::integral_constant<int, 0>{}, item); break;
+        case 1: run_tile(std::integral_constant<int, 1>{}, item); break;
+        case 2: run_tile(std::integral_constant<int, 2>{}, item); break;
+        case 3: run_tile(std::integral_constant<int, 3>{}, item); break;
+        default: run_tile(std::integral_constant<int, 4>{}, item); break;
       }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync();  // no CTA of the pair leaves (or frees TMEM) while its peer may still touch it
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN)
@@ -342,30 +386,44 @@ int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs&
     rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, BK, 128);
   if (rc) return rc;
   if (!B_MN)
-    rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, BK, BN, 128);
+    rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, BK, BN / CTAS, 128);
   else
     rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, BK, 128);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CTAS>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
-  const int grid = items < cb_sm_count() ? items : cb_sm_count();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  if constexpr (CTAS == 1) {
+    const int grid = items < cb_sm_count() ? items : cb_sm_count();
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    const int pairs = cb_sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)(items < pairs ? items : pairs));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   CB_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, GemmArgs& p,
                    cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(A, lda, B, ldb, p, s);
-  if (!a_mn && b_mn) return launch<BN, false, true>(A, lda, B, ldb, p, s);
-  if (a_mn && b_mn) return launch<BN, true, true>(A, lda, B, ldb, p, s);
-  return launch<BN, true, false>(A, lda, B, ldb, p, s);
+  if (!a_mn && !b_mn) return launch<BN, false, false, CTAS>(A, lda, B, ldb, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true, CTAS>(A, lda, B, ldb, p, s);
+  if (a_mn && b_mn) return launch<BN, true, true, CTAS>(A, lda, B, ldb, p, s);
+  return launch<BN, true, false, CTAS>(A, lda, B, ldb, p, s);
 }
 
 }  // namespace
@@ -388,6 +446,12 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
                    (aux == nullptr || ldaux % 8 == 0),
                "gemm: epilogue leading dimensions must keep 16-byte row alignment");
 
+  {
+    const long long lim = (1ll << 31) - 1;
+    const long long rows = (long long)M + 2 * BM;  // tile overhang is never dereferenced but is multiplied
+    CB_CHECK_ARG(rows * ldo < lim && rows * ldo2 < lim && rows * ldr < lim && rows * ldaux < lim,
+                 "gemm: epilogue tensors must stay below 2^31 elements (32-bit epilogue offsets)");
+  }
   GemmArgs p;
   p.M = M, p.N = N, p.K = K;
   p.num_kb = (K + BK - 1) / BK;
@@ -402,13 +466,14 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
   // Tile width and split-K factor from a small cost model (clocks per CTA): a k-block costs the slower of the MMA
   // (135 clk per 128 x 256 x 16 instruction) and of its operand bytes at the per-SM share of the L2 -> SM bandwidth
   // (~42 B/clk: B300_MICROARCH.md "LTS throughput cap" / 148 SMs), plus a fixed per-item prologue / epilogue.
-  auto plan = [&](int c, int want_splits, int& out_splits, int& out_kb_per_split) {
-    const long long tiles = (long long)p.num_m_tiles * ((N + c - 1) / c);
+  auto plan = [&](int c, int ctas, int want_splits, int& out_splits, int& out_kb_per_split) {
+    const int workers = sms / ctas;
+    const long long tiles = (long long)((M + BM * ctas - 1) / (BM * ctas)) * ((N + c - 1) / c);
     int sp = want_splits;
     if (sp <= 0) {
       sp = 1;
-      if (accumulate && tiles < sms) {  // wgrad-like: few tiles, long contraction -> split K
-        sp = (int)(sms / tiles);
+      if (accumulate && tiles < workers) {  // wgrad-like: few tiles, long contraction -> split K
+        sp = (int)(workers / tiles);
         const int max_splits = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;
         if (sp > max_splits) sp = max_splits;
       }
@@ -418,25 +483,38 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
     sp = (p.num_kb + kbs - 1) / kbs;
     out_splits = sp, out_kb_per_split = kbs;
     const long long items = tiles * sp;
-    const long long waves = (items + sms - 1) / sms;
+    const long long waves = (items + workers - 1) / workers;
     const double t_mma = 542.0 * c / 256.0;
-    const double t_load = (16384.0 + 128.0 * c) / 42.0;
+    const double t_load = (16384.0 + 128.0 * c / ctas) / 42.0;
     const double t_kb = t_mma > t_load ? t_mma : t_load;
     return (double)waves * (kbs * t_kb + 1500.0 + 6.0 * c);
   };
-  int bn = block_n, splits = 1;
-  if (bn != 64 && bn != 128 && bn != 256) {
+  static const int force_ctas = [] {
+    const char* e = getenv("CB_GEMM_CTAS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  int bn = block_n, ctas = 1, splits = 1;
+  {
     double best = 1e30;
     const int cands[3] = {256, 128, 64};
     for (int i = 0; i < 3; ++i) {
       const int c = cands[i];
-      if (c > 64 && N <= c / 2) continue;
-      int sp, kbs;
-      const double cost = plan(c, split_k, sp, kbs);
-      if (cost < best) best = cost, bn = c;
+      if (block_n == 64 || block_n == 128 || block_n == 256) {
+        if (c != block_n) continue;
+      } else if (c > 64 && N <= c / 2) {
+        continue;
+      }
+      for (int g = 1; g <= 2; ++g) {
+        if (g == 2 && (c == 64 || M <= BM)) continue;  // pairs: 256-row tiles, B halves of at least 64 columns
+        if (force_ctas != 0 && g != force_ctas && !(force_ctas == 2 && (c == 64 || M <= BM))) continue;
+        int sp, kbs;
+        const double cost = plan(c, g, split_k, sp, kbs);
+        if (cost < best) best = cost, bn = c, ctas = g;
+      }
     }
   }
-  plan(bn, split_k, splits, p.kb_per_split);
+  plan(bn, ctas, split_k, splits, p.kb_per_split);
+  p.num_m_tiles = (M + BM * ctas - 1) / (BM * ctas);
   p.num_n_tiles = (N + bn - 1) / bn;
   p.splits = splits;
   CB_CHECK_ARG(splits == 1 || accumulate, "gemm: split-K needs accumulate=1 (fp32 atomics into a zeroed/accumulated out)");
@@ -444,9 +522,13 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
                "gemm: split-K supports no bias/residual/activation");
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ctas == 2) {
+    if (bn == 256) return dispatch_major<256, 2>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    return dispatch_major<128, 2>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+  }
   switch (bn) {
-    case 256: return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
-    case 128: return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
-    default: return dispatch_major<64>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    case 256: return dispatch_major<256, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    case 128: return dispatch_major<128, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+    default: return dispatch_major<64, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
   }
 }
