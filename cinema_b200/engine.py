@@ -317,6 +317,50 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
 
 
 # ------------------------------------------------------------------------------------------
+# per-view concurrency
+# ------------------------------------------------------------------------------------------
+_SIDE_STREAMS: dict[tuple, list] = {}
+
+
+class ViewStreams:
+    """Fork / join of per-view work onto side streams.
+
+    The views of a frame-set (SAX + 3 LAX) are independent until their tokens are concatenated, and the LAX kernels
+    are far too small to fill 148 SMs (a 12 x 12 token grid per sample), so view i > 0 runs on side stream i - 1
+    while view 0 stays on the caller's stream.  Every fork starts with ``side.wait_stream(main)`` and ``join()``
+    makes the caller's stream wait for the side streams: memory handed between streams is always ordered, and the
+    pattern is capturable in a CUDA graph (the side streams join the capture through the fork event)."""
+
+    def __init__(self, device: torch.device, enabled: bool = True) -> None:
+        self.enabled = enabled and device.type == "cuda"
+        self.used: list = []
+        if self.enabled:
+            self.main = torch.cuda.current_stream(device)
+            key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(3)]
+            self.pool = _SIDE_STREAMS[key]
+
+    def view(self, i: int):
+        """Context manager for the work of view ``i``."""
+        import contextlib
+
+        if not self.enabled or i == 0:
+            return contextlib.nullcontext()
+        st = self.pool[(i - 1) % len(self.pool)]
+        st.wait_stream(self.main)
+        if st not in self.used:
+            self.used.append(st)
+        return torch.cuda.stream(st)
+
+    def join(self) -> None:
+        if self.enabled:
+            for st in self.used:
+                self.main.wait_stream(st)
+            self.used = []
+
+
+# ------------------------------------------------------------------------------------------
 # small helpers
 # ------------------------------------------------------------------------------------------
 _ARANGE_CACHE: dict[tuple, torch.Tensor] = {}

@@ -153,6 +153,7 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32)
     st.embed = []
     off = 1
     offs = []
+    vs = engine.ViewStreams(dev)
     for i, v in enumerate(views):
         down = model.enc_down_dict[v]
         nk = n_keeps[i]
@@ -160,16 +161,18 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32)
         ps = tuple(down.patch_sizes[-1])
         src, sgrid, sidx = sources[i][-1]
         e_in = src.shape[1] * math.prod(ps)
-        p16 = torch.empty((b * nk, e_in), dtype=BF16, device=dev)
-        _C.gather_patches(src, sgrid, ps, sidx, True, p16)
         w_pe = _lin_of(arena, down.patch_embed.proj, train)
         w_li = _lin_of(arena, down.linear, train)
-        t1 = engine.linear_fwd(p16, w_pe)
-        t2 = engine.linear_fwd(t1, w_li, out_dtype=F32)
-        pos = down.interpolate_pos_encoding(model_grid(model, v, sources[i])).data.reshape(-1, d).contiguous()
-        _C.embed_rows(t2.view(b, nk, d), 0, None, pos, keep[i], b, nk, out=x0, out_off=off)
+        with vs.view(i):  # views write disjoint token rows of x0
+            p16 = torch.empty((b * nk, e_in), dtype=BF16, device=dev)
+            _C.gather_patches(src, sgrid, ps, sidx, True, p16)
+            t1 = engine.linear_fwd(p16, w_pe)
+            t2 = engine.linear_fwd(t1, w_li, out_dtype=F32)
+            pos = down.interpolate_pos_encoding(model_grid(model, v, sources[i])).data.reshape(-1, d).contiguous()
+            _C.embed_rows(t2.view(b, nk, d), 0, None, pos, keep[i], b, nk, out=x0, out_off=off)
         st.embed.append((p16, t1, w_pe, w_li, ps))
         off += nk
+    vs.join()
     st.offs = offs
 
     st.enc_w = [engine.blockw(arena, blk, train) for blk in model.encoder.blocks]
@@ -192,29 +195,32 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32)
     st.fusion = []
     foff = b
     foffs = []
+    idx_rows = [engine.arange_idx(b, offs[i], n_keeps[i], dev) for i in range(len(views))]
     for i, v in enumerate(views):
         fus = model.enc_fusion_dict[v]
         nk = n_keeps[i]
         foffs.append(foff)
-        xv = torch.empty((b, nk, d), dtype=F32, device=dev)
-        _C.gather_rows(enc3, engine.arange_idx(b, offs[i], nk, dev), xv)
-        cur_v = xv.view(b * nk, d)
-        lv = []
-        for lvl, conv in enumerate(fus.down_convs):
-            k = tuple(conv.kernel_size)
-            skip, sgrid, sidx = sources[i][lvl]
-            pf = torch.empty((b * nk, skip.shape[1] * math.prod(k)), dtype=BF16, device=dev)
-            _C.gather_patches(skip, sgrid, k, sidx, False, pf)
-            wc = _lin_of(arena, conv, train)
-            cur_v = engine.linear_fwd(pf, wc, out_dtype=F32, residual=cur_v)
-            lv.append((pf, wc, k))
         nw = engine.normw(arena, fus.norm, train)
-        y16 = _rows(f16, foff, b * nk)
-        _, y32, mean, rstd = engine.ln_fwd(cur_v, nw, want32=want_fused32, stats=train, y16=y16)
+        wcs = [_lin_of(arena, conv, train) for conv in fus.down_convs]
+        with vs.view(i):  # views write disjoint row segments of f16
+            xv = torch.empty((b, nk, d), dtype=F32, device=dev)
+            _C.gather_rows(enc3, idx_rows[i], xv)
+            cur_v = xv.view(b * nk, d)
+            lv = []
+            for lvl, conv in enumerate(fus.down_convs):
+                k = tuple(conv.kernel_size)
+                skip, sgrid, sidx = sources[i][lvl]
+                pf = torch.empty((b * nk, skip.shape[1] * math.prod(k)), dtype=BF16, device=dev)
+                _C.gather_patches(skip, sgrid, k, sidx, False, pf)
+                cur_v = engine.linear_fwd(pf, wcs[lvl], out_dtype=F32, residual=cur_v)
+                lv.append((pf, wcs[lvl], k))
+            y16 = _rows(f16, foff, b * nk)
+            _, y32, mean, rstd = engine.ln_fwd(cur_v, nw, want32=want_fused32, stats=train, y16=y16)
         if want_fused32:
             fused32[v] = y32.view(b, nk, d)
         st.fusion.append((lv, nw, cur_v if train else None, mean, rstd))
         foff += b * nk
+    vs.join()
     st.foffs = foffs
     return f16, fused32, st
 
@@ -227,17 +233,21 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
     n, d = st.n, st.d
     denc = torch.empty((b, n, d), dtype=F32, device=dev)
     _C.scatter_rows(d_f32[:b].view(b, 1, d), engine.arange_idx(b, 0, 1, dev), denc)
+    idx_rows = [engine.arange_idx(b, st.offs[i], n_keeps[i], dev) for i in range(len(views))]
+    vs = engine.ViewStreams(dev)
     for i, _ in enumerate(views):
         nk = n_keeps[i]
         lv, nw, cur_v, mean, rstd = st.fusion[i]
         dyv = _rows(d_f32, st.foffs[i], b * nk)
-        dcur32, dcur16 = engine.ln_bwd(dyv, cur_v, mean, rstd, nw)
-        _C.scatter_rows(dcur32.view(b, nk, d), engine.arange_idx(b, st.offs[i], nk, dev), denc)
-        for lvl, (pf, wc, k) in enumerate(lv):
-            tgt = targets[i][lvl]
-            dpf = engine.linear_bwd(dcur16, pf, wc, need_dx=tgt is not None)
-            if tgt is not None:
-                _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
+        with vs.view(i):  # disjoint rows of denc, per-view parameters and gradient targets
+            dcur32, dcur16 = engine.ln_bwd(dyv, cur_v, mean, rstd, nw)
+            _C.scatter_rows(dcur32.view(b, nk, d), idx_rows[i], denc)
+            for lvl, (pf, wc, k) in enumerate(lv):
+                tgt = targets[i][lvl]
+                dpf = engine.linear_bwd(dcur16, pf, wc, need_dx=tgt is not None)
+                if tgt is not None:
+                    _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
+    vs.join()
     ew = st.enc_w
     gb_of = lambda j: engine.fusable_bias(ew[j].fc2, d) if j >= 0 else None  # noqa: E731
     dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm,
@@ -253,13 +263,15 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
     for i, _ in enumerate(views):
         nk = n_keeps[i]
         p16, t1, w_pe, w_li, ps = st.embed[i]
-        dt2 = torch.empty((b, nk, d), dtype=BF16, device=dev)
-        _C.embed_rows(dx0, st.offs[i], None, None, None, b, nk, out16=dt2)
-        dt1 = engine.linear_bwd(dt2.view(b * nk, d), t1, w_li)
-        tgt = targets[i][-1] if targets[i] else None
-        dp = engine.linear_bwd(dt1, p16, w_pe, need_dx=tgt is not None)
-        if tgt is not None:
-            _C.scatter_patches(dp, tgt[0], tgt[1], ps, tgt[2], True, accumulate=True)
+        with vs.view(i):  # left open on purpose: the caller continues with the stem backward of view i, then joins
+            dt2 = torch.empty((b, nk, d), dtype=BF16, device=dev)
+            _C.embed_rows(dx0, st.offs[i], None, None, None, b, nk, out16=dt2)
+            dt1 = engine.linear_bwd(dt2.view(b * nk, d), t1, w_li)
+            tgt = targets[i][-1] if targets[i] else None
+            dp = engine.linear_bwd(dt1, p16, w_pe, need_dx=tgt is not None)
+            if tgt is not None:
+                _C.scatter_patches(dp, tgt[0], tgt[1], ps, tgt[2], True, accumulate=True)
+    return vs
 
 
 
@@ -275,6 +287,7 @@ def _build_sources(model, arena, views, imgs32, skips, keep, masks, slot, grids,
     """Gather sources of every view (see :func:`_encode`): the native visible-only stem when the view's stem is the
     reference default (layer norm), else the dense feature maps computed by the caller (cuDNN path)."""
     sources, stems = [], []
+    vs = engine.ViewStreams(imgs32[0].device)
     for i, v in enumerate(views):
         down = model.enc_down_dict[v]
         src = _Sources()
@@ -288,14 +301,17 @@ def _build_sources(model, arena, views, imgs32, skips, keep, masks, slot, grids,
             stems.append(None)
         else:
             levels = stem.stem_weights(arena, down, train)
-            geo = stem.Geometry(keep[i], masks[i].contiguous(), slot[i], grids[i], b, n_keeps[i])
-            outs, saved = stem.stem_fwd(levels, imgs32[i], geo, train)
+            mask_i = masks[i].contiguous()
+            with vs.view(i):
+                geo = stem.Geometry(keep[i], mask_i, slot[i], grids[i], b, n_keeps[i])
+                outs, saved = stem.stem_fwd(levels, imgs32[i], geo, train)
             t = b * n_keeps[i]
             unit = (1,) * len(grids[i])
             for lw, x in zip(levels, outs):
                 src.append((stem.level_view(x, t, lw.f), unit, None))
             stems.append((levels, geo, saved))
         sources.append(src)
+    vs.join()
     return sources, stems
 
 
@@ -420,21 +436,26 @@ class _MAEFn(torch.autograd.Function):
         acc[:, 3:5] = float("-inf")
         preds, diffs, heads, dvs = [], [], [], []
         sq_counts, patch_counts = [], []
+        q_rows = [engine.arange_idx(b, qoffs[i], n_masks[i], dev) if n_masks[i] > 0 else None for i in range(nv)]
+        masks_c = [m.contiguous() for m in masks]
+        vs = engine.ViewStreams(dev)
         for i, v in enumerate(views):
             nm = n_masks[i]
             w_ph = _lin_of(arena, model.pred_head_dict[v], train)
             e = w_ph.n
-            dv16 = torch.empty((b, nm, dd), dtype=BF16, device=dev)
-            pred = torch.empty((b, nm, e), dtype=F32, device=dev)
-            diff = torch.empty((b, nm, e), dtype=F32, device=dev) if train else None
-            if nm > 0:
-                _C.gather_rows(dec3, engine.arange_idx(b, qoffs[i], nm, dev), dv16)
-                engine.linear_fwd(dv16.view(b * nm, dd), w_ph, out=pred.view(b * nm, e))
-            _C.masked_mse_fwd(imgs32[i], tuple(model.dec_patch_size_dict[v]), masks[i].contiguous(), slot[i], pred,
-                              bool(model.norm_target), 1e-6, acc[i], diff)
+            with vs.view(i):  # per-view head, loss accumulators acc[i]
+                dv16 = torch.empty((b, nm, dd), dtype=BF16, device=dev)
+                pred = torch.empty((b, nm, e), dtype=F32, device=dev)
+                diff = torch.empty((b, nm, e), dtype=F32, device=dev) if train else None
+                if nm > 0:
+                    _C.gather_rows(dec3, q_rows[i], dv16)
+                    engine.linear_fwd(dv16.view(b * nm, dd), w_ph, out=pred.view(b * nm, e))
+                _C.masked_mse_fwd(imgs32[i], tuple(model.dec_patch_size_dict[v]), masks_c[i], slot[i], pred,
+                                  bool(model.norm_target), 1e-6, acc[i], diff)
             preds.append(pred), diffs.append(diff), heads.append(w_ph), dvs.append(dv16)
             sq_counts.append(b * nm * e)
             patch_counts.append(b * math.prod(grids[i]))
+        vs.join()
         out = torch.empty(1 + 5 * nv, dtype=F32, device=dev)
         scales = torch.empty(nv, dtype=F32, device=dev)
         _C.mae_loss_finalize(acc, sq_counts, patch_counts, out, scales)
@@ -460,15 +481,19 @@ class _MAEFn(torch.autograd.Function):
         dev = g_loss.device
         sc = (s["scales"] * g_loss.to(F32)).contiguous()
         ddec = torch.zeros((b, nq, dd), dtype=BF16, device=dev)
+        q_rows = [engine.arange_idx(b, s["qoffs"][i], n_masks[i], dev) if n_masks[i] > 0 else None for i in range(len(views))]
+        vs = engine.ViewStreams(dev)
         for i, _ in enumerate(views):
             nm = n_masks[i]
             if nm == 0:
                 continue
             diff = s["diffs"][i]
-            dpred = torch.empty(diff.shape, dtype=BF16, device=dev)
-            _C.scale_cast(diff, dpred, sc[i:i + 1])
-            ddv = engine.linear_bwd(dpred.view(b * nm, -1), s["dvs"][i].view(b * nm, dd), s["heads"][i])
-            _C.scatter_rows(ddv.view(b, nm, dd), engine.arange_idx(b, s["qoffs"][i], nm, dev), ddec)
+            with vs.view(i):  # disjoint query rows of ddec
+                dpred = torch.empty(diff.shape, dtype=BF16, device=dev)
+                _C.scale_cast(diff, dpred, sc[i:i + 1])
+                ddv = engine.linear_bwd(dpred.view(b * nm, -1), s["dvs"][i].view(b * nm, dd), s["heads"][i])
+                _C.scatter_rows(ddv.view(b, nm, dd), q_rows[i], ddec)
+        vs.join()
         dec_w = s["dec_w"]
         dgb_of = lambda j: engine.fusable_bias(dec_w[j].fc2, dd) if j >= 0 else None  # noqa: E731
         dx32, dx16 = engine.ln_bwd(ddec.view(b * nq, dd), s["dec_last"], s["dmean"], s["drstd"], s["dec_norm"],
@@ -521,11 +546,13 @@ class _MAEFn(torch.autograd.Function):
                 _C.colsum_seg(dxq, s["qoffs"][i], nm, arena.grad_view(mt).view(-1))
         d_f32 = engine.linear_bwd(dy16, s["f16"], s["w_dl"], dx_dtype=F32)
         targets, dskips = _build_targets(views, s["sources"], s["stems"], s["skips"], s["needs"])
-        _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets)
+        vs = _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets)
         for i, stem_state in enumerate(s["stems"]):
             if stem_state is not None:
                 levels, geo, saved = stem_state
-                stem.stem_bwd(levels, geo, saved, [t[0] for t in _native_grad_buffers(targets[i])])
+                with vs.view(i):  # same side stream as the embedding backward of this view
+                    stem.stem_bwd(levels, geo, saved, [t[0] for t in _native_grad_buffers(targets[i])])
+        vs.join()
         flat = [g for per_view in dskips for g in per_view]
         return (None, None, None, None, None, None, *flat)
 
