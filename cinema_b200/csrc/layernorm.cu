@@ -333,6 +333,150 @@ ln_bwd_tma_kernel(const void* __restrict__ dy_, long long lddy, const float* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Short rows (the ConvMAE stem: D = 64 / 128 channels, ~150 k rows): LPR = D / 4 lanes own one row (one float4
+// each), a warp works on 32 / LPR rows at once and keeps UNR independent row groups in flight, reductions are
+// LPR-wide shuffles.  The per-column sums (dgamma, dbeta, dxsum) of a lane's four columns live in registers.
+// ------------------------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int UNR>
+__global__ void __launch_bounds__(256) ln_fwd_small_kernel(const float* __restrict__ x, long long ldx,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int M, float eps, bf16* __restrict__ y16, long long ldy16,
+                                                           float* __restrict__ y32, long long ldy32,
+                                                           float* __restrict__ mean_o, float* __restrict__ rstd_o, int act) {
+  constexpr int RPW = 32 / LPR;  // rows per warp pass
+  const int lane = threadIdx.x & 31;
+  const int c = lane % LPR;      // float4 column of this lane
+  const int rsub = lane / LPR;
+  const float inv_d = 1.0f / (float)(4 * LPR);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + c);
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = wid * (RPW * UNR); base < M; base += nw * (RPW * UNR)) {
+    float4 v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = base + u * RPW + rsub;
+      v[u] = row < M ? __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = base + u * RPW + rsub;
+      const float mean = group_sum<LPR>((v[u].x + v[u].y) + (v[u].z + v[u].w)) * inv_d;
+      const float a0 = v[u].x - mean, a1 = v[u].y - mean, a2 = v[u].z - mean, a3 = v[u].w - mean;
+      const float rstd = rsqrtf(group_sum<LPR>(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3) * inv_d + eps);
+      if (row < M) {
+        if (c == 0) {
+          if (mean_o) mean_o[row] = mean;
+          if (rstd_o) rstd_o[row] = rstd;
+        }
+        float4 o = make_float4(fmaf(a0 * rstd, g.x, bb.x), fmaf(a1 * rstd, g.y, bb.y), fmaf(a2 * rstd, g.z, bb.z),
+                               fmaf(a3 * rstd, g.w, bb.w));
+        if (act) o.x = gelu_f(o.x), o.y = gelu_f(o.y), o.z = gelu_f(o.z), o.w = gelu_f(o.w);
+        if (y32) reinterpret_cast<float4*>(y32 + row * ldy32)[c] = o;
+        if (y16) reinterpret_cast<uint2*>(y16 + row * ldy16)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+template <int LPR, int UNR, bool DY_BF16>
+__global__ void __launch_bounds__(256)
+ln_bwd_small_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
+                    const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
+                    const float* __restrict__ dres, long long lddres, int M, float* __restrict__ dx32, long long lddx32,
+                    bf16* __restrict__ dx16, long long lddx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ dxsum, const float* __restrict__ beta_act) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int D = 4 * LPR;
+  const int lane = threadIdx.x & 31;
+  const int c = lane % LPR;
+  const int rsub = lane / LPR;
+  const float inv_d = 1.0f / (float)D;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  float4 bt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (beta_act != nullptr) bt = __ldg(reinterpret_cast<const float4*>(beta_act) + c);
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, dxs = dg;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = wid * (RPW * UNR); base < M; base += nw * (RPW * UNR)) {
+    float4 xv[UNR], d[UNR], rs[UNR];
+    float mean[UNR], rstd[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = base + u * RPW + rsub;
+      xv[u] = d[u] = rs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mean[u] = 0.f, rstd[u] = 0.f;
+      if (row < M) {
+        xv[u] = __ldg(reinterpret_cast<const float4*>(x + row * ldx) + c);
+        if (DY_BF16) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + row * lddy) + c);
+          const float2 a = unpack_bf16(w.x), b = unpack_bf16(w.y);
+          d[u] = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          d[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + row * lddy) + c);
+        }
+        if (dres) rs[u] = __ldg(reinterpret_cast<const float4*>(dres + row * lddres) + c);
+        mean[u] = __ldg(mean_i + row), rstd[u] = __ldg(rstd_i + row);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = base + u * RPW + rsub;
+      const float nmr = -mean[u] * rstd[u];
+      const float4 xh = make_float4(fmaf(xv[u].x, rstd[u], nmr), fmaf(xv[u].y, rstd[u], nmr), fmaf(xv[u].z, rstd[u], nmr),
+                                    fmaf(xv[u].w, rstd[u], nmr));
+      float4 dd = d[u];
+      if (beta_act != nullptr) {  // the forward applied GELU to the LN output
+        dd.x *= gelu_grad_f(fmaf(xh.x, g.x, bt.x)), dd.y *= gelu_grad_f(fmaf(xh.y, g.y, bt.y));
+        dd.z *= gelu_grad_f(fmaf(xh.z, g.z, bt.z)), dd.w *= gelu_grad_f(fmaf(xh.w, g.w, bt.w));
+      }
+      const float4 dyg = make_float4(dd.x * g.x, dd.y * g.y, dd.z * g.z, dd.w * g.w);
+      const float m1r = group_sum<LPR>((dyg.x + dyg.y) + (dyg.z + dyg.w)) * inv_d * rstd[u];
+      const float m2r = -group_sum<LPR>(fmaf(dyg.x, xh.x, fmaf(dyg.y, xh.y, fmaf(dyg.z, xh.z, dyg.w * xh.w)))) * inv_d * rstd[u];
+      if (row < M) {
+        dg.x = fmaf(dd.x, xh.x, dg.x), dg.y = fmaf(dd.y, xh.y, dg.y), dg.z = fmaf(dd.z, xh.z, dg.z), dg.w = fmaf(dd.w, xh.w, dg.w);
+        db.x += dd.x, db.y += dd.y, db.z += dd.z, db.w += dd.w;
+        float4 o;
+        o.x = fmaf(xh.x, m2r, fmaf(dyg.x, rstd[u], -m1r)) + rs[u].x;
+        o.y = fmaf(xh.y, m2r, fmaf(dyg.y, rstd[u], -m1r)) + rs[u].y;
+        o.z = fmaf(xh.z, m2r, fmaf(dyg.z, rstd[u], -m1r)) + rs[u].z;
+        o.w = fmaf(xh.w, m2r, fmaf(dyg.w, rstd[u], -m1r)) + rs[u].w;
+        if (dx32) reinterpret_cast<float4*>(dx32 + row * lddx32)[c] = o;
+        const uint2 pk = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (dx16) reinterpret_cast<uint2*>(dx16 + row * lddx16)[c] = pk;
+        const float2 a = unpack_bf16(pk.x), b = unpack_bf16(pk.y);
+        dxs.x += a.x, dxs.y += a.y, dxs.z += b.x, dxs.w += b.y;
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr && dxsum == nullptr) return;
+  __shared__ float sred[3 * D];
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  atomicAdd(&sred[4 * c + 0], dg.x), atomicAdd(&sred[4 * c + 1], dg.y), atomicAdd(&sred[4 * c + 2], dg.z), atomicAdd(&sred[4 * c + 3], dg.w);
+  atomicAdd(&sred[D + 4 * c + 0], db.x), atomicAdd(&sred[D + 4 * c + 1], db.y), atomicAdd(&sred[D + 4 * c + 2], db.z), atomicAdd(&sred[D + 4 * c + 3], db.w);
+  if (dxsum != nullptr) {
+    atomicAdd(&sred[2 * D + 4 * c + 0], dxs.x), atomicAdd(&sred[2 * D + 4 * c + 1], dxs.y);
+    atomicAdd(&sred[2 * D + 4 * c + 2], dxs.z), atomicAdd(&sred[2 * D + 4 * c + 3], dxs.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sred[i]);
+    if (dbeta) atomicAdd(dbeta + i, sred[D + i]);
+    if (dxsum) atomicAdd(dxsum + i, sred[2 * D + i]);
+  }
+}
+
 inline int pick_nv(int D) {
   const int need = (D / 4 + 31) / 32;
   const int opts[] = {1, 2, 4, 6, 8, 12, 16};
@@ -359,6 +503,20 @@ extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamm
   const int nv = pick_nv(D);
   const int blocks = (int)min((long long)(M + 7) / 8, (long long)cb_sm_count() * 8);
   cudaStream_t s = (cudaStream_t)stream;
+  if (D == 16 || D == 32 || D == 64 || D == 128) {  // short rows: several rows per warp pass
+    constexpr int UNR = 4;
+    const long long rows_per_block = 8ll * (128 / D) * UNR;
+    const int sb = (int)min((M + rows_per_block - 1) / rows_per_block, (long long)cb_sm_count() * 8);
+#define LN_FWD_SMALL(L) \
+  ln_fwd_small_kernel<L, UNR><<<sb, 256, 0, s>>>(x, ldx, gamma, beta, M, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)
+    if (D == 16) LN_FWD_SMALL(4);
+    else if (D == 32) LN_FWD_SMALL(8);
+    else if (D == 64) LN_FWD_SMALL(16);
+    else LN_FWD_SMALL(32);
+#undef LN_FWD_SMALL
+    CB_LAUNCH_CHECK();
+    return 0;
+  }
   switch (nv) {
     LN_DISPATCH(1, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
     LN_DISPATCH(2, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
@@ -388,7 +546,29 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
   const size_t dy_row = (size_t)D * (bf ? 2 : 4);
   const bool aligned = dy_row % 16 == 0 && ((size_t)lddy * (bf ? 2 : 4)) % 16 == 0 && ((uintptr_t)dy & 15) == 0 &&
                        ((uintptr_t)x & 15) == 0 && (dres == nullptr || (((uintptr_t)dres & 15) == 0 && lddres % 4 == 0));
-  // short rows: per-row bulk copies are too small; very long rows: the per-lane accumulators spill -> register-cached kernel
+  if (D == 16 || D == 32 || D == 64 || D == 128) {  // short rows (stem): several rows per warp pass, fused column sums
+    constexpr int UNR = 4;
+    const long long rows_per_block = 8ll * (128 / D) * UNR;
+    const int sb = (int)min((M + rows_per_block - 1) / rows_per_block, (long long)cb_sm_count() * 4);
+#define LN_BWD_SMALL(L)                                                                                             \
+  do {                                                                                                              \
+    if (bf)                                                                                                         \
+      ln_bwd_small_kernel<L, UNR, true><<<sb, 256, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
+                                                           lddx32, (bf16*)dx16, lddx16, dgamma, dbeta, dxsum, beta_act); \
+    else                                                                                                            \
+      ln_bwd_small_kernel<L, UNR, false><<<sb, 256, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
+                                                            lddx32, (bf16*)dx16, lddx16, dgamma, dbeta, dxsum, beta_act); \
+  } while (0)
+    if (D == 16) LN_BWD_SMALL(4);
+    else if (D == 32) LN_BWD_SMALL(8);
+    else if (D == 64) LN_BWD_SMALL(16);
+    else LN_BWD_SMALL(32);
+#undef LN_BWD_SMALL
+    CB_LAUNCH_CHECK();
+    return 0;
+  }
+  // mid-length rows go through the TMA-staged kernel; very long rows (per-lane accumulators would spill) and unaligned
+  // ones through the register-cached kernel
   if (aligned && nv > 0 && D >= 256 && D <= 1024) {
     const int slot_bytes = (int)(((size_t)D * 8 + dy_row + 127) / 128 * 128);
     int stages = (int)((size_t)200 * 1024 / ((size_t)LNB_WARPS * slot_bytes));
@@ -424,7 +604,7 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
       return 0;
     }
   }
-  CB_CHECK_ARG(dxsum == nullptr, "layernorm_bwd: dxsum needs 256 <= D <= 1024 and 16-byte aligned rows (TMA-staged path)");
+  CB_CHECK_ARG(dxsum == nullptr, "layernorm_bwd: dxsum needs D in {16, 32, 64, 128} or 256 <= D <= 1024 with 16-byte aligned rows (TMA-staged path)");
   // few, fat blocks: every block ends with 2*D global atomics for dgamma / dbeta
   const int blocks = (int)min((long long)(M + 7) / 8, (long long)cb_sm_count() * 2);
   const size_t smem = 2 * (size_t)D * sizeof(float);

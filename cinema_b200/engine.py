@@ -152,8 +152,8 @@ def ln_fwd(x32: torch.Tensor, w: NormW, *, want16: bool = True, want32: bool = F
 
 def fusable_bias(w: "LinW | None", d: int) -> torch.Tensor | None:
     """Bias-gradient target of ``w`` if the LayerNorm backward can accumulate it (``dxsum``: TMA-staged path,
-    256 <= D <= 1024 with 16-byte bf16 rows)."""
-    return w.gb if (w is not None and w.gb is not None and d % 8 == 0 and 256 <= d <= 1024) else None
+    short-row kernel for D in {16, 32, 64, 128}, TMA-staged path for 256 <= D <= 1024)."""
+    return w.gb if (w is not None and w.gb is not None and (d in (16, 32, 64, 128) or (d % 8 == 0 and 256 <= d <= 1024))) else None
 
 
 def ln_bwd(dy: torch.Tensor, x32: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, w: NormW, *,

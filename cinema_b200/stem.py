@@ -167,8 +167,9 @@ def stem_bwd(levels: list[LevelW], geo: Geometry, saved, dlevels: list[torch.Ten
                                     out_bias=gb_of(bi - 1))
             bsaved[bi] = None
         # LayerNorm + GELU backward (dy of the patch conv), then the conv's wgrad / dgrad
-        _, dy16 = engine.ln_bwd(dx32, y, mean, rstd, lw.norm, dx32=dx32, beta_act=lw.norm.beta)
-        drows = engine.linear_bwd(dy16, rows, lw.conv, need_dx=li > 0)
+        conv_gb = engine.fusable_bias(lw.conv, lw.chans)
+        _, dy16 = engine.ln_bwd(dx32, y, mean, rstd, lw.norm, dx32=dx32, beta_act=lw.norm.beta, dxsum=conv_gb)
+        drows = engine.linear_bwd(dy16, rows, lw.conv, need_dx=li > 0, bias_done=conv_gb is not None)
         if li > 0:
             pw = levels[li - 1]
             _C.scatter_patches(drows, level_view(dlevels[li - 1], t, pw.f), lw.f, lw.patch, None, False, accumulate=True)

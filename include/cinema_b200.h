@@ -88,7 +88,7 @@ int cb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const fl
  * dx = LN'(dy) (+ dres if given) -> dx32 (fp32) and optional bf16 copy dx16; dgamma / dbeta are
  * accumulated with fp32 atomics (may be NULL).  dy is bf16 (dy_dtype=CB_DT_BF16) or fp32.
  * dxsum (may be NULL): dxsum[c] += sum over rows of bf16(dx[row, c]) -- the bias gradient of the Linear layer whose
- * output gradient is dx16 (fuses the column-sum pass; needs 256 <= D <= 1024 and 16-byte aligned rows). */
+ * output gradient is dx16 (fuses the column-sum pass; needs D in {16,32,64,128} or 256 <= D <= 1024 with 16-byte aligned rows). */
 int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, const float* x, long long ldx, const float* mean,
                      const float* rstd, const float* gamma, const float* dres, long long lddres, int M, int D,
                      float* dx32, long long lddx32, void* dx16, long long lddx16, float* dgamma, float* dbeta,
