@@ -405,7 +405,8 @@ struct BwdCfg {
   static constexpr int OFF_P = OFF_DO + 2 * TILE_BYTES;
   static constexpr int OFF_DS = OFF_P + PS_BYTES;
   static constexpr int OFF_VEC = OFF_DS + PS_BYTES;       // lse / delta: [2 stages][2][128] floats
-  static constexpr int OFF_BAR = OFF_VEC + 2 * 2 * 128 * 4;
+  static constexpr int OFF_STG = OFF_VEC + 2 * 2 * 128 * 4;  // dQ drain transposition: 8 warps x (32 rows x 64 B)
+  static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 256 + D, TM_DQ = 256 + 2 * D;
 };
@@ -556,20 +557,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     float* dq_g = p.dq_acc + ((long long)b * p.H + h) * p.Nq * D;
 
-    auto drain_dq = [&](int i) {  // dQ tile i: lanes = query rows, this warpgroup takes D/2 columns
-      const int q_row = i * 128 + r;
+    // dQ tile i: TMEM lanes = query rows, this warpgroup takes D/2 columns.  The accumulator chunk (thread == row, 16
+    // fp32) goes through a per-warp swizzled smem tile so that each fp32 reduction instruction covers 8 rows x 64
+    // contiguous bytes (whole sectors) instead of 32 rows x 16 bytes: the L2 reduction rate, not the tensor pipe,
+    // bounds this kernel, and it is counted in sector requests.
+    const uint32_t stg = smem_u32(smem + C::OFF_STG + warp * 2048);
+    const int sub = lane >> 2, c16 = lane & 3;
+    auto drain_dq = [&](int i) {
+      const int row0 = i * 128 + (warp & 3) * 32;  // first query row of this warp
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(lane_addr + C::TM_DQ + wg * (D / 2) + c * 16, v);
         tmem_ld_wait();
-        if (q_row < p.Nq) {
-          float* dst = dq_g + (long long)q_row * D + wg * (D / 2) + c * 16;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            red_add_v4f(dst + 4 * g, __uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                        __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                       "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rr = k * 8 + sub;
+          float x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
+                       : "r"(stg + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4)));
+          const int q_row = row0 + rr;
+          if (q_row < p.Nq) red_add_v4f(dq_g + (long long)q_row * D + wg * (D / 2) + c * 16 + c16 * 4, x0, x1, x2, x3);
         }
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();

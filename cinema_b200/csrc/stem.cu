@@ -232,7 +232,7 @@ __device__ __forceinline__ void load_row(const bf16* __restrict__ in, const int 
 }
 
 template <int F, int ND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)  // <= 128 registers: 16 warps per SM hide the L2 latency of the row loads
 dwconv_fast_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const bf16* __restrict__ w,
                    const float* __restrict__ bias, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
                    const int* __restrict__ keep, DwGeom g, int flip) {
@@ -406,10 +406,10 @@ int launch_fast_fwd(const void* in, void* out, const void* w, const float* bias,
     configured = smem;
   }
   const long long tasks = (long long)g.B * g.nk * (g.C / 64);
-  long long blocks = (tasks + 7) / 8;
+  long long blocks = (tasks + 3) / 4;
   const long long cap = (long long)cb_sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, 256, smem, stream>>>((const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot, keep, g,
+  kern<<<(unsigned)blocks, 128, smem, stream>>>((const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot, keep, g,
                                                transpose);
   CB_LAUNCH_CHECK();
   return 0;
