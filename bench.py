@@ -198,19 +198,27 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
 
         setattr(_C, name, timed)
 
+    from cinema_b200 import engine
+
     names = ["gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16",
              "mask_to_index", "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize",
-             "gather_patches", "scatter_patches", "masked_mse_fwd", "sumsq", "adamw_flat"]
+             "gather_patches", "scatter_patches", "masked_mse_fwd", "sumsq", "adamw_flat", "dwconv_tokens",
+             "dwconv_tokens_wgrad", "expand_token_index"]
     for n in names:
         wrap(n)
+    engine.VIEW_STREAMS_ENABLED = False  # one stream: every kernel's event pair brackets that kernel alone
     try:
         s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        # park the GPU so that the host (~0.2 ms of Python / ctypes per launch) runs ahead: the launches then execute
+        # back to back and each event pair measures device time only
+        torch.cuda._sleep(int(6e8))
         s_all.record()
         trainer.eager_step(batch_dev)
         e_all.record()
         torch.cuda.synchronize()
     finally:
+        engine.VIEW_STREAMS_ENABLED = True
         for n, fn in originals.items():
             setattr(_C, n, fn)
     agg: dict[str, list[float]] = {}
@@ -221,7 +229,8 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
         a[2] += 1
     total = s_all.elapsed_time(e_all)
     own = sum(a[0] for a in agg.values())
-    return {"step_ms": total, "own_kernels_ms": own, "stem_and_other_ms": total - own,
+    return {"step_ms": total, "own_kernels_ms": own, "torch_and_gaps_ms": total - own,
+            "note": "one eager step on a single stream, launches queued behind a GPU-side sleep; CUDA events per C-ABI launch",
             "kernels": {k: {"ms": round(v[0], 3), "launches": v[2], "tflops": round(v[1] / v[0] / 1e9, 1) if v[0] > 0 and v[1] else None}
                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}}
 
@@ -350,10 +359,26 @@ def main() -> None:
     if prof is not None:
         g = prof["kernels"].get("gemm")
         if g and g["tflops"]:
+            traffic = None
+            tp = ROOT / "profiles" / "gemm_traffic.json"  # written by tools/summarize_launches.py from an ncu capture
+            if tp.exists():
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             line["roofline"] = {"bound": "tensor", "achieved": g["tflops"], "peak": sustained, "unit": "TFLOP/s",
-                                "frac": round(g["tflops"] / sustained, 4), "traffic": None,
-                                "kernel": "gemm_bf16_kernel (all GEMM launches of one step, CUDA events per launch)",
-                                "share_of_step": round(g["ms"] / prof["step_ms"], 3), "peak_kind": f"{peak_kind} sustained"}
+                                "frac": round(g["tflops"] / sustained, 4), "traffic": traffic,
+                                "kernel": "gemm_bf16_kernel (tcgen05 GEMM, all launches of one step: algorithmic 2MNK FLOPs "
+                                          "of a launch / its CUDA-event duration, averaged over the step's launches)",
+                                "launches_per_step": g["launches"], "avg_launch_us": round(1e3 * g["ms"] / g["launches"], 2),
+                                "avg_gflop_per_launch": round(g["tflops"] * g["ms"] / g["launches"], 2),
+                                "share_of_step": round(g["ms"] / (ms / args.steps), 3), "peak_kind": f"{peak_kind} sustained"}
+            a_f, a_b = prof["kernels"].get("attention_fwd"), prof["kernels"].get("attention_bwd")
+            if a_f and a_b:
+                line["attention_roofline"] = {"bound": "tensor", "fwd_tflops": a_f["tflops"], "bwd_tflops": a_b["tflops"],
+                                              "peak": sustained, "unit": "TFLOP/s",
+                                              "frac": round((a_f["tflops"] * a_f["ms"] + a_b["tflops"] * a_b["ms"]) /
+                                                            (a_f["ms"] + a_b["ms"]) / sustained, 4),
+                                              "share_of_step": round((a_f["ms"] + a_b["ms"]) / (ms / args.steps), 3),
+                                              "note": "tcgen05 flash attention (head_dim 64 encoder / 32 decoder); "
+                                                      "4 BHNqNkd fwd, 8 BHNqNkd bwd credited"}
         line["kernel_profile"] = prof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(kw, 2, 2, 1)

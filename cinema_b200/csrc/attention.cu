@@ -10,10 +10,10 @@
 //   warps 0-3 / 4-7 : softmax warpgroup for query tile t = 0 / 1, one query row per thread
 //             (thread == TMEM lane, so row max / row sum need no shuffles): S row TMEM -> registers,
 //             online softmax in the log2 domain with lazy rescaling of O (only when the running max
-//             grows by more than 2^8), P -> bf16 -> 128B-swizzled smem as the A operand of P.V.
+//             grows by more than 2^8), P -> bf16 -> TMEM (tcgen05.st) as the A operand of P.V.
 // The two query tiles ping-pong on the tensor pipe: S_t(j+1) is issued as soon as warpgroup t has
 // pulled S_t(j) into registers, so the tensor core runs under the exp / max / sum work.
-// TMEM: S0 | S1 (128 cols each) | O0 | O1 (head_dim cols each).
+// TMEM: S0 | S1 (128 cols each) | P0 | P1 (64 cols each, packed bf16) | O0 | O1 (head_dim cols each).
 #include "../../include/cinema_b200.h"
 #include "common.cuh"
 
@@ -39,14 +39,13 @@ struct FwdCfg {
   static constexpr uint64_t SWZ = D == 64 ? UMMA_SW128 : UMMA_SW64;
   static constexpr int GROUP_BYTES = 8 * ROW_BYTES;           // 8-row swizzle group (SBO)
   static constexpr int TILE_BYTES = TQ * ROW_BYTES;           // Q / K / V tile
-  static constexpr int P_BYTES = TQ * TK * 2;                 // 32 KB, two 64-column chunks of 16 KB
   static constexpr int OFF_Q = 0;                             // 2 tiles
   static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;        // 2 stages
   static constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;        // 2 stages
-  static constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;        // 2 tiles
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * TILE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_O = 256;                          // column of O0; O1 at +D
+  static constexpr int TMEM_P = 256;                          // P0 as packed bf16 (64 columns); P1 at +64
+  static constexpr int TMEM_O = 384;                          // column of O0; O1 at +D
 };
 
 // 1-D bulk copy global -> shared, completion (bytes) on an mbarrier
@@ -143,7 +142,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t q_base = smem_u32(smem + C::OFF_Q);
       const uint32_t k_base = smem_u32(smem + C::OFF_K);
       const uint32_t v_base = smem_u32(smem + C::OFF_V);
-      const uint32_t p_base = smem_u32(smem + C::OFF_P);
       auto issue_s = [&](int t, int j) {
         const uint32_t ks = k_base + (j & 1) * C::TILE_BYTES;
         const uint32_t qs = q_base + t * C::TILE_BYTES;
@@ -177,12 +175,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int t = 0; t < n_tiles_q; ++t) {
           mbar_wait(&p_full[t], j & 1);
           tcgen05_fence_after();
-          const uint32_t ps = p_base + t * C::P_BYTES;
+          // A = P_t straight from TMEM (16 keys = 8 packed columns per step): an smem A operand would cost 4 KB of
+          // shared-memory reads per instruction and pace these narrow (N = head_dim) MMAs at ~64 clk each
 #pragma unroll
           for (int kk = 0; kk < TK / 16; ++kk) {
-            const uint64_t da = umma_smem_desc(ps + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
             const uint64_t db = umma_smem_desc(vs + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
-            umma_bf16_ss(tmem_base + C::TMEM_O + t * D, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_base + C::TMEM_O + t * D, tmem_base + C::TMEM_P + t * 64 + kk * 8, db, idesc_o,
+                         (j > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&pv_done[t]);
         }
@@ -198,7 +197,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = (warp & 3) * 32 + lane;  // row inside the tile == TMEM lane
     if (t < n_tiles_q) {
       const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      uint8_t* p_smem = smem + C::OFF_P + t * C::P_BYTES;
       float m_ref = -INFINITY;  // reference max (log2 domain) the accumulators are expressed against
       float l = 0.f;
       const float sc = p.scale_log2;
@@ -260,17 +258,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float neg_m = -m_ref;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int vcol = 0; vcol < TK / 8; ++vcol) {
-          float e[8];
+        for (int blk = 0; blk < TK / 32; ++blk) {  // 32 keys -> 16 packed columns of this row's P in TMEM
+          uint32_t pw[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(s[vcol * 8 + i], sc, neg_m));
-          sum4[0] += e[0] + e[1], sum4[1] += e[2] + e[3], sum4[2] += e[4] + e[5], sum4[3] += e[6] + e[7];
-          const uint4 pk = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
-                                      pack_bf16(e[6], e[7]));
-          *reinterpret_cast<uint4*>(p_smem + (vcol >> 3) * 16384 + sw128_vec_offset(r, vcol & 7)) = pk;
+          for (int w = 0; w < 16; w += 2) {
+            const int i0 = blk * 32 + w * 2;
+            const float e0 = ex2_approx(fmaf(s[i0], sc, neg_m)), e1 = ex2_approx(fmaf(s[i0 + 1], sc, neg_m));
+            const float e2 = ex2_approx(fmaf(s[i0 + 2], sc, neg_m)), e3 = ex2_approx(fmaf(s[i0 + 3], sc, neg_m));
+            sum4[0] += e0, sum4[1] += e1, sum4[2] += e2, sum4[3] += e3;
+            pw[w] = pack_bf16(e0, e1), pw[w + 1] = pack_bf16(e2, e3);
+          }
+          tmem_st_32x32b_x16(lane_addr + C::TMEM_P + t * 64 + blk * 16, pw);
         }
+        tmem_st_wait();
         l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        fence_proxy_async_smem();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);

@@ -320,6 +320,7 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
 # per-view concurrency
 # ------------------------------------------------------------------------------------------
 _SIDE_STREAMS: dict[tuple, list] = {}
+VIEW_STREAMS_ENABLED = True  # bench.py turns this off for its per-kernel instrumented step (serial launches)
 
 
 class ViewStreams:
@@ -332,7 +333,7 @@ class ViewStreams:
     pattern is capturable in a CUDA graph (the side streams join the capture through the fork event)."""
 
     def __init__(self, device: torch.device, enabled: bool = True) -> None:
-        self.enabled = enabled and device.type == "cuda"
+        self.enabled = enabled and VIEW_STREAMS_ENABLED and device.type == "cuda"
         self.used: list = []
         if self.enabled:
             self.main = torch.cuda.current_stream(device)
