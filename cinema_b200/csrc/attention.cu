@@ -366,14 +366,14 @@ extern "C" int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, l
 //   dP^T = V dO_i^T                                                        SS, both K-major
 //   P^T  = exp2(S^T * scale*log2e - lse_q * log2e)            \  two warpgroups, one key row per
 //   dS^T = P^T o (dP^T - delta_q) * scale                     /  thread, 64 query columns each
-//   dV  += P^T  dO_i          A = P^T smem (K-major),  B = dO_i tile read MN-major
-//   dK  += dS^T Q_i           A = dS^T smem (K-major), B = Q_i  tile read MN-major
+//   dV  += P^T  dO_i          A = P^T in TMEM (packed bf16, TS-mode MMA), B = dO_i tile read MN-major
+//   dK  += dS^T Q_i           A = dS^T in TMEM (head_dim 32) or smem (K-major), B = Q_i tile read MN-major
 //   dQ_i = dS   K             A = dS^T smem read MN-major, B = K tile read MN-major
 // dQ_i is drained from TMEM with fp32 red.global.add into dq_acc (summed over key tiles by the
 // atomics) and converted to bf16 by a small follow-up kernel; dK / dV are written once at the end.
 // The same Q_i / dO_i / K smem tiles serve as K-major and as MN-major operands: only the UMMA
 // descriptors differ, nothing is transposed in memory.
-// TMEM: S^T (128) | dP^T (128) | dV (D) | dK (D) | dQ (D).
+// TMEM: S^T (128) | dP^T (128) | P^T (64, packed) | [dS^T (64, packed)] | dV (D) | dK (D) | dQ (D).
 // ============================================================================================
 namespace {
 
@@ -398,18 +398,22 @@ struct BwdCfg {
   static constexpr uint64_t SWZ = D == 64 ? UMMA_SW128 : UMMA_SW64;
   static constexpr int GROUP_BYTES = 8 * ROW_BYTES;
   static constexpr int TILE_BYTES = 128 * ROW_BYTES;
-  static constexpr int PS_BYTES = 128 * 128 * 2;  // P^T or dS^T, two 64-column chunks of 16 KB
+  static constexpr int PS_BYTES = 128 * 128 * 2;  // dS^T, two 64-column chunks of 16 KB
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;        // 2 stages
   static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES;   // 2 stages
-  static constexpr int OFF_P = OFF_DO + 2 * TILE_BYTES;
-  static constexpr int OFF_DS = OFF_P + PS_BYTES;
+  static constexpr int OFF_DS = OFF_DO + 2 * TILE_BYTES;
   static constexpr int OFF_VEC = OFF_DS + PS_BYTES;       // lse / delta: [2 stages][2][128] floats
   static constexpr int OFF_STG = OFF_VEC + 2 * 2 * 128 * 4;  // dQ drain transposition: 8 warps x (32 rows x 64 B)
   static constexpr int OFF_BAR = OFF_STG + 8 * 2048;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 256 + D, TM_DQ = 256 + 2 * D;
+  // A operands in TMEM (TS-mode MMA): P^T always; dS^T too when the 512 columns allow it (head_dim 32).  An smem A
+  // operand costs a 4 KB shared-memory read per K=16 step, which paces these narrow (N = head_dim) MMAs at ~64 clk.
+  static constexpr bool DS_TMEM = D <= 32;
+  static constexpr int TM_S = 0, TM_DP = 128, TM_PT = 256, TM_DST = 320;
+  static constexpr int TM_DV = DS_TMEM ? 384 : 320, TM_DK = TM_DV + D, TM_DQ = TM_DV + 2 * D;
+  static_assert(TM_DQ + D <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
@@ -494,7 +498,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t v_base = smem_u32(smem + C::OFF_V);
       const uint32_t q_base = smem_u32(smem + C::OFF_Q);
       const uint32_t do_base = smem_u32(smem + C::OFF_DO);
-      const uint32_t p_base = smem_u32(smem + C::OFF_P);
       const uint32_t ds_base = smem_u32(smem + C::OFF_DS);
       auto issue_s_dp = [&](int i) {
         const uint32_t qs = q_base + (i & 1) * C::TILE_BYTES;
@@ -527,16 +530,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t qs = q_base + (i & 1) * C::TILE_BYTES;
         const uint32_t dos = do_base + (i & 1) * C::TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // dV += P^T dO_i
-          const uint64_t da = umma_smem_desc(p_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
+        for (int kk = 0; kk < 8; ++kk) {  // dV += P^T dO_i        (A = P^T from TMEM, 16 queries = 8 packed columns)
           const uint64_t db = umma_smem_desc(dos + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
-          umma_bf16_ss(tmem_base + C::TM_DV, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + C::TM_DV, tmem_base + C::TM_PT + kk * 8, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // dK += dS^T Q_i
-          const uint64_t da = umma_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
           const uint64_t db = umma_smem_desc(qs + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
-          umma_bf16_ss(tmem_base + C::TM_DK, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          if constexpr (C::DS_TMEM) {
+            umma_bf16_ts(tmem_base + C::TM_DK, tmem_base + C::TM_DST + kk * 8, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
+            umma_bf16_ss(tmem_base + C::TM_DK, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+          }
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // dQ_i = dS K   (A = dS^T read MN-major: M = queries contiguous)
@@ -594,7 +600,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (lane == 0) mbar_arrive(dq_free);
     };
 
-    const uint32_t p_s32 = smem_u32(smem + C::OFF_P + wg * 16384);
     const uint32_t ds_s32 = smem_u32(smem + C::OFF_DS + wg * 16384);
     for (int i = 0; i < n_q; ++i) {
       // -lse*log2e and delta*scale of this tile's 128 queries arrive with the Q / dO stage (bulk copies)
@@ -644,16 +649,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tcgen05_fence_after();
         drain_dq(i - 1);
       }
+      // P^T (and dS^T for head_dim 32) -> TMEM as packed bf16: this warpgroup's 64 queries = 32 columns
+      tmem_st_32x32b_x32(lane_addr + C::TM_PT + wg * 32, pk);
+      if constexpr (C::DS_TMEM) tmem_st_32x32b_x32(lane_addr + C::TM_DST + wg * 32, dsk);
 #pragma unroll
-      for (int vcol = 0; vcol < 8; ++vcol) {
+      for (int vcol = 0; vcol < 8; ++vcol) {  // dS^T -> smem: dQ = dS K reads it transposed (MN-major A)
         const uint32_t off = sw128_vec_offset(r, vcol);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_s32 + off), "r"(pk[4 * vcol]), "r"(pk[4 * vcol + 1]),
-                     "r"(pk[4 * vcol + 2]), "r"(pk[4 * vcol + 3])
-                     : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s32 + off), "r"(dsk[4 * vcol]),
                      "r"(dsk[4 * vcol + 1]), "r"(dsk[4 * vcol + 2]), "r"(dsk[4 * vcol + 3])
                      : "memory");
       }
+      tmem_st_wait();
       fence_proxy_async_smem();
       tcgen05_fence_before();
       __syncwarp();
