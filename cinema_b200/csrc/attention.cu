@@ -603,8 +603,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t ds_s32 = smem_u32(smem + C::OFF_DS + wg * 16384);
     for (int i = 0; i < n_q; ++i) {
       // -lse*log2e and delta*scale of this tile's 128 queries arrive with the Q / dO stage (bulk copies)
-      const float4* nl4 = reinterpret_cast<const float4*>(vec + (i & 1) * 256) + wg * 16;
-      const float4* ds4 = nl4 + 32;
+      const uint32_t nl_s32 = smem_u32(vec + (i & 1) * 256) + wg * 256;  // this warpgroup's 64 queries (16 float4)
+      const uint32_t ds_v32 = nl_s32 + 512;
       float s[64], dp[64];
       mbar_wait(s_full, i & 1);
       tcgen05_fence_after();
@@ -634,7 +634,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint32_t pk[32], dsk[32];  // packed bf16 P^T and dS^T of this row half
 #pragma unroll
       for (int g = 0; g < 16; ++g) {
-        const float4 nl = nl4[g], dsv = ds4[g];
+        float4 nl, dsv;  // explicit shared-memory loads (broadcast): a generic LD here serialises on its latency
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nl.x), "=f"(nl.y), "=f"(nl.z), "=f"(nl.w) : "r"(nl_s32 + g * 16));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dsv.x), "=f"(dsv.y), "=f"(dsv.z), "=f"(dsv.w) : "r"(ds_v32 + g * 16));
         const float p0 = ex2_approx(fmaf(s[4 * g + 0], p.scale_log2, nl.x));
         const float p1 = ex2_approx(fmaf(s[4 * g + 1], p.scale_log2, nl.y));
         const float p2 = ex2_approx(fmaf(s[4 * g + 2], p.scale_log2, nl.z));
