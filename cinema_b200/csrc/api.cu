@@ -7,6 +7,8 @@
 #include "../../include/cinema_b200.h"
 #include "common.cuh"
 
+#include <cstdlib>
+
 static thread_local char g_err[1024] = "";
 
 void cb_set_error(const char* fmt, ...) {
@@ -100,4 +102,12 @@ int cb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   uint64_t strides[1] = {pitch_bytes};
   uint32_t box[2] = {box_inner, box_outer};
   return cb_make_tmap_nd(out, base, 2, dims, strides, box, swizzle_bytes);
+}
+
+bool cb_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CB_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }

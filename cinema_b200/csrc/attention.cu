@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdArgs p) {
   using C = FwdCfg<D>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -112,6 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: setup done, wait for the kernels that produce Q / K / V (/ dO) before the first load
 
   if (warp >= 8) {
    // the light warpgroup hands registers to the softmax warpgroups (8 x 232 + 4 x 40 == 12 x 168)
@@ -333,7 +335,7 @@ int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
     attr_set = true;
   }
   dim3 grid((a.Nq + 2 * TQ - 1) / (2 * TQ), a.H, a.B);
-  kern<<<grid, FWD_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, a);
+  cb_launch(kern, grid, FWD_THREADS, C::SMEM_BYTES, stream, tq, tk, tv, a);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -426,6 +428,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const AttnBwdArgs p) {
   using C = BwdCfg<D>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -466,6 +469,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: setup done, wait for the kernels that produce Q / K / V (/ dO) before the first load
 
   if (warp >= 8) {
    // the light warpgroup hands registers to the compute warpgroups (8 x 232 + 4 x 40 == 12 x 168)
@@ -715,6 +719,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, lo
                                   const bf16* __restrict__ d_o, long long do_sb, long long do_sn, long long do_sh,
                                   const float* __restrict__ lse, float* __restrict__ nl2, float* __restrict__ dsc, int B,
                                   int H, int Nq, int NqP, float scale) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long row = gid >> 3;  // over B * H * NqP
   const int sub = (int)(gid & 7);
@@ -752,6 +757,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, lo
 template <int D>
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long sb, long long sn,
                                        long long sh, int B, int H, int Nq) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int VPR = D / 8;  // 16-byte output vectors per row
   const long long row = gid / VPR;
@@ -774,7 +780,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   using C = BwdCfg<D>;
   const long long rows = (long long)a.B * a.H * a.Nq;
   const long long rows_p = (long long)a.B * a.H * a.NqP;
-  attn_delta_kernel<D><<<(unsigned)((rows_p * 8 + 255) / 256), 256, 0, stream>>>(
+  cb_launch(attn_delta_kernel<D>, (unsigned)((rows_p * 8 + 255) / 256), 256, 0, stream, 
       o, o_sb, o_sn, o_sh, d_o, do_sb, do_sn, do_sh, lse, const_cast<float*>(a.nl2), const_cast<float*>(a.dsc), a.B, a.H, a.Nq,
       a.NqP, a.scale);
   CB_LAUNCH_CHECK();
@@ -786,10 +792,10 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
     attr_set = true;
   }
   dim3 grid((a.Nk + 127) / 128, a.H, a.B);
-  kern<<<grid, BWD_THREADS, C::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, a);
+  cb_launch(kern, grid, BWD_THREADS, C::SMEM_BYTES, stream, tq, tk, tv, tdo, a);
   CB_LAUNCH_CHECK();
   const long long vecs = rows * (D / 8);
-  attn_dq_convert_kernel<D><<<(unsigned)((vecs + 255) / 256), 256, 0, stream>>>(a.dq_acc, dq, dq_sb, dq_sn, dq_sh, a.B,
+  cb_launch(attn_dq_convert_kernel<D>, (unsigned)((vecs + 255) / 256), 256, 0, stream, a.dq_acc, dq, dq_sb, dq_sn, dq_sh, a.B,
                                                                                 a.H, a.Nq);
   CB_LAUNCH_CHECK();
   return 0;

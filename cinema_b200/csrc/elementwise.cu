@@ -25,6 +25,7 @@ struct NdGeom {
 // fp32 -> bf16 flat cast
 // ---------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long n8 = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -44,6 +45,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
 // ---------------------------------------------------------------------------------------
 __global__ void mask_to_index_kernel(const unsigned char* __restrict__ mask, int B, int n, int n_keep,
                                      int* __restrict__ keep_idx, int* __restrict__ drop_idx, int* __restrict__ slot) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -80,6 +82,7 @@ template <bool SCATTER>
 __global__ void move_rows_kernel(const uint4* __restrict__ src, long long src_bstride, long long src_off,
                                  const int* __restrict__ idx, int B, int k, uint4* __restrict__ dst,
                                  long long dst_bstride, long long dst_off, int vec_per_row) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * k) return;
@@ -103,6 +106,7 @@ __global__ void embed_rows_kernel(const float4* __restrict__ a, long long a_bstr
                                   const float4* __restrict__ rowv, const float4* __restrict__ table,
                                   const int* __restrict__ idx, int B, int k, int vec_per_row, float4* __restrict__ out,
                                   uint2* __restrict__ out16, long long out_bstride, long long out_off) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * k) return;
@@ -129,6 +133,7 @@ __global__ void embed_rows_kernel(const float4* __restrict__ a, long long a_bstr
 // out[d] += sum over (b, i<k) of X[b*bstride + off + i, d]   (fp32; token / bias style gradients)
 __global__ void colsum_seg_f32_kernel(const float* __restrict__ X, long long bstride, long long off, int B, int k, int D,
                                       float* __restrict__ out, int rows_per_block) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= D) return;
   const long long total = (long long)B * k;
@@ -146,6 +151,7 @@ __global__ void colsum_seg_f32_kernel(const float* __restrict__ X, long long bst
 // dst = bf16(src * scale_host * (scale_dev ? *scale_dev : 1))
 __global__ void scale_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n,
                                   const float* __restrict__ scale_dev, float scale) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -165,6 +171,7 @@ __global__ void scale_cast_kernel(const float* __restrict__ src, bf16* __restric
 template <typename T, bool INVERSE>
 __global__ void patchify_kernel(const T* __restrict__ src, T* __restrict__ dst, NdGeom g, long long n_per_batch,
                                 long long total) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const long long b = e / n_per_batch;
@@ -200,6 +207,7 @@ __global__ void patchify_kernel(const T* __restrict__ src, T* __restrict__ dst, 
 template <typename TS, typename TR, bool SCATTER>
 __global__ void patches_kernel(TS* __restrict__ img, TR* __restrict__ rows, NdGeom g, const int* __restrict__ idx,
                                int k, int chan_last, long long total, int accumulate) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long stride = (long long)gridDim.x * blockDim.x;
   int pprod = 1;
 #pragma unroll
@@ -243,6 +251,7 @@ __global__ void patches_kernel(TS* __restrict__ img, TR* __restrict__ rows, NdGe
 // ---------------------------------------------------------------------------------------
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ X, long long ldx, int M, int N, float* __restrict__ out,
                                    int rows_per_block) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   __shared__ float2 part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 64 + lane * 2;
@@ -274,6 +283,7 @@ template <typename T>
 __global__ void rope_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ cos_t,
                             const float* __restrict__ sin_t, long long rows, int n_tokens, int H, int d, int ro,
                             float sin_sign) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int half = ro >> 1;
   const long long total = rows * d;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -330,7 +340,7 @@ inline int blocks_for(long long work, int threads) {
 extern "C" int cb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   if (n <= 0) return 0;
   CB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "cast: buffers must be 16-byte aligned");
-  cast_f32_bf16_kernel<<<blocks_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  cb_launch(cast_f32_bf16_kernel, blocks_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -338,7 +348,7 @@ extern "C" int cb_cast_f32_bf16(const float* src, void* dst, long long n, void* 
 extern "C" int cb_mask_to_index(const unsigned char* mask, int B, int n, int n_keep, int* keep_idx, int* drop_idx,
                                 int* slot, void* stream) {
   CB_CHECK_ARG(B > 0 && n > 0 && n_keep >= 0 && n_keep <= n, "mask_to_index: bad sizes B=%d n=%d keep=%d", B, n, n_keep);
-  mask_to_index_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(mask, B, n, n_keep, keep_idx, drop_idx, slot);
+  cb_launch(mask_to_index_kernel, (B + 3) / 4, 128, 0, (cudaStream_t)stream, mask, B, n, n_keep, keep_idx, drop_idx, slot);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -348,7 +358,7 @@ extern "C" int cb_gather_rows(const void* src, long long src_bstride, const int*
   if (B <= 0 || k <= 0) return 0;
   CB_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "gather_rows: row_bytes %lld must be a multiple of 16", row_bytes);
   const long long rows = (long long)B * k;
-  move_rows_kernel<false><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  cb_launch(move_rows_kernel<false>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, 
       (const uint4*)src, src_bstride, 0, idx, B, k, (uint4*)out, out_bstride, out_off, (int)(row_bytes / 16));
   CB_LAUNCH_CHECK();
   return 0;
@@ -359,7 +369,7 @@ extern "C" int cb_scatter_rows(const void* src, long long src_bstride, long long
   if (B <= 0 || k <= 0) return 0;
   CB_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0, "scatter_rows: row_bytes %lld must be a multiple of 16", row_bytes);
   const long long rows = (long long)B * k;
-  move_rows_kernel<true><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  cb_launch(move_rows_kernel<true>, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, 
       (const uint4*)src, src_bstride, src_off, idx, B, k, (uint4*)dst, dst_bstride, 0, (int)(row_bytes / 16));
   CB_LAUNCH_CHECK();
   return 0;
@@ -372,7 +382,7 @@ extern "C" int cb_embed_rows_f32(const float* a, long long a_bstride, long long 
   CB_CHECK_ARG(D > 0 && D % 4 == 0, "embed_rows: D=%d must be a multiple of 4", D);
   CB_CHECK_ARG(out != nullptr || out16 != nullptr, "embed_rows: no output given");
   const long long rows = (long long)B * k;
-  embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  cb_launch(embed_rows_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, 
       (const float4*)a, a_bstride, a_off, (const float4*)row, (const float4*)table, idx, B, k, D / 4, (float4*)out,
       (uint2*)out16, out_bstride, out_off);
   CB_LAUNCH_CHECK();
@@ -391,14 +401,14 @@ extern "C" int cb_patchify(const void* src, void* dst, int B, int C, int ndim, c
   cudaStream_t s = (cudaStream_t)stream;
   if (elem_bytes == 4) {
     if (!inverse)
-      patchify_kernel<float, false><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, g, per_batch, total);
+      cb_launch(patchify_kernel<float, false>, blocks, 256, 0, s, (const float*)src, (float*)dst, g, per_batch, total);
     else
-      patchify_kernel<float, true><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, g, per_batch, total);
+      cb_launch(patchify_kernel<float, true>, blocks, 256, 0, s, (const float*)src, (float*)dst, g, per_batch, total);
   } else {
     if (!inverse)
-      patchify_kernel<uint16_t, false><<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
+      cb_launch(patchify_kernel<uint16_t, false>, blocks, 256, 0, s, (const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
     else
-      patchify_kernel<uint16_t, true><<<blocks, 256, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
+      cb_launch(patchify_kernel<uint16_t, true>, blocks, 256, 0, s, (const uint16_t*)src, (uint16_t*)dst, g, per_batch, total);
   }
   CB_LAUNCH_CHECK();
   return 0;
@@ -423,9 +433,9 @@ extern "C" int cb_gather_patches(const void* src, int src_dtype, long long sb, l
   const int blocks = blocks_for(total, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (src_dtype == CB_DT_F32)
-    patches_kernel<const float, bf16, false><<<blocks, 256, 0, s>>>((const float*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
+    cb_launch(patches_kernel<const float, bf16, false>, blocks, 256, 0, s, (const float*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
   else
-    patches_kernel<const bf16, bf16, false><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
+    cb_launch(patches_kernel<const bf16, bf16, false>, blocks, 256, 0, s, (const bf16*)src, (bf16*)out, g, idx, k, chan_last, total, 0);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -441,13 +451,13 @@ extern "C" int cb_scatter_patches(const void* rows, int rows_dtype, void* dst, i
   const int blocks = blocks_for(total, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_BF16)
-    patches_kernel<bf16, const bf16, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
+    cb_launch(patches_kernel<bf16, const bf16, true>, blocks, 256, 0, s, (bf16*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
   else if (rows_dtype == CB_DT_BF16 && dst_dtype == CB_DT_F32)
-    patches_kernel<float, const bf16, true><<<blocks, 256, 0, s>>>((float*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
+    cb_launch(patches_kernel<float, const bf16, true>, blocks, 256, 0, s, (float*)dst, (const bf16*)rows, g, idx, k, chan_last, total, accumulate);
   else if (rows_dtype == CB_DT_F32 && dst_dtype == CB_DT_F32)
-    patches_kernel<float, const float, true><<<blocks, 256, 0, s>>>((float*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
+    cb_launch(patches_kernel<float, const float, true>, blocks, 256, 0, s, (float*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
   else
-    patches_kernel<bf16, const float, true><<<blocks, 256, 0, s>>>((bf16*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
+    cb_launch(patches_kernel<bf16, const float, true>, blocks, 256, 0, s, (bf16*)dst, (const float*)rows, g, idx, k, chan_last, total, accumulate);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -461,7 +471,7 @@ extern "C" int cb_colsum_bf16(const void* X, long long ldx, int M, int N, float*
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
-  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)X, ldx, M, N, out,
+  cb_launch(colsum_bf16_kernel, dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream, (const bf16*)X, ldx, M, N, out,
                                                                                       rows_per_block);
   CB_LAUNCH_CHECK();
   return 0;
@@ -477,7 +487,7 @@ extern "C" int cb_colsum_seg_f32(const float* X, long long bstride_rows, long lo
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (int)((total + row_blocks - 1) / row_blocks);
   row_blocks = (total + rows_per_block - 1) / rows_per_block;
-  colsum_seg_f32_kernel<<<dim3(col_blocks, (unsigned)row_blocks), 128, 0, (cudaStream_t)stream>>>(
+  cb_launch(colsum_seg_f32_kernel, dim3(col_blocks, (unsigned)row_blocks), 128, 0, (cudaStream_t)stream, 
       X, bstride_rows, off, B, k, D, out, rows_per_block);
   CB_LAUNCH_CHECK();
   return 0;
@@ -487,7 +497,7 @@ extern "C" int cb_scale_cast_bf16(const float* src, void* dst, long long n, cons
                                   void* stream) {
   if (n <= 0) return 0;
   CB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "scale_cast: buffers must be 16/8-byte aligned");
-  scale_cast_kernel<<<blocks_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n, scale_dev, scale);
+  cb_launch(scale_cast_kernel, blocks_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n, scale_dev, scale);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -502,9 +512,9 @@ extern "C" int cb_rope_apply(const void* x, void* y, int dtype, const float* cos
   const int blocks = blocks_for(rows * d, 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CB_DT_F32)
-    rope_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, (float*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
+    cb_launch(rope_kernel<float>, blocks, 256, 0, s, (const float*)x, (float*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
   else
-    rope_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
+    cb_launch(rope_kernel<bf16>, blocks, 256, 0, s, (const bf16*)x, (bf16*)y, cos_t, sin_t, rows, n_tokens, H, d, rotary_dim, sgn);
   CB_LAUNCH_CHECK();
   return 0;
 }

@@ -80,6 +80,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();  // the next kernel may be scheduled as SMs drain; it waits for this grid before reading
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -105,6 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barriers, TMEM and descriptors are set up: now wait for the producer kernels of A / B / residual
 
   const int tiles = p.num_m_tiles * p.num_n_tiles;  // pair: num_m_tiles counts 256-row tiles
   const int items = tiles * p.splits;
@@ -399,7 +401,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs&
   const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
   if constexpr (CTAS == 1) {
     const int grid = items < cb_sm_count() ? items : cb_sm_count();
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+    cb_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, p);
   } else {
     const int pairs = cb_sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
@@ -407,10 +409,12 @@ int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs&
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = cb_pdl_enabled() ? 2 : 1;
     CB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   }
   CB_LAUNCH_CHECK();

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      int M, int D, float eps, bf16* __restrict__ y16, long long ldy16,
                                                      float* __restrict__ y32, long long ldy32, float* __restrict__ mean_o,
                                                      float* __restrict__ rstd_o, int act) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = D >> 2;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy
                                                      long long lddx32, bf16* __restrict__ dx16, long long lddx16,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      const float* __restrict__ beta_act) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nvec = D >> 2;
@@ -188,6 +190,7 @@ ln_bwd_tma_kernel(const void* __restrict__ dy_, long long lddy, const float* __r
                   long long lddx32, bf16* __restrict__ dx16, long long lddx16, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, float* __restrict__ dxsum, const float* __restrict__ beta_act, int stages,
                   int slot_bytes) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ __align__(128) uint8_t lsm[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(256) ln_fwd_small_kernel(const float* __restri
                                                            int M, float eps, bf16* __restrict__ y16, long long ldy16,
                                                            float* __restrict__ y32, long long ldy32,
                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o, int act) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   constexpr int RPW = 32 / LPR;  // rows per warp pass
   const int lane = threadIdx.x & 31;
   const int c = lane % LPR;      // float4 column of this lane
@@ -396,6 +400,7 @@ ln_bwd_small_kernel(const void* __restrict__ dy_, long long lddy, const float* _
                     const float* __restrict__ dres, long long lddres, int M, float* __restrict__ dx32, long long lddx32,
                     bf16* __restrict__ dx16, long long lddx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     float* __restrict__ dxsum, const float* __restrict__ beta_act) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   constexpr int RPW = 32 / LPR;
   constexpr int D = 4 * LPR;
   const int lane = threadIdx.x & 31;
@@ -508,7 +513,7 @@ extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamm
     const long long rows_per_block = 8ll * (128 / D) * UNR;
     const int sb = (int)min((M + rows_per_block - 1) / rows_per_block, (long long)cb_sm_count() * 8);
 #define LN_FWD_SMALL(L) \
-  ln_fwd_small_kernel<L, UNR><<<sb, 256, 0, s>>>(x, ldx, gamma, beta, M, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)
+  cb_launch(ln_fwd_small_kernel<L, UNR>, sb, 256, 0, s, x, ldx, gamma, beta, M, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)
     if (D == 16) LN_FWD_SMALL(4);
     else if (D == 32) LN_FWD_SMALL(8);
     else if (D == 64) LN_FWD_SMALL(16);
@@ -518,13 +523,13 @@ extern "C" int cb_layernorm_fwd(const float* x, long long ldx, const float* gamm
     return 0;
   }
   switch (nv) {
-    LN_DISPATCH(1, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(2, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(4, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(6, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(8, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(12, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
-    LN_DISPATCH(16, (ln_fwd_kernel<NV><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(1, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(2, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(4, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(6, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(8, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(12, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
+    LN_DISPATCH(16, (cb_launch(ln_fwd_kernel<NV>, blocks, 256, 0, s, x, ldx, gamma, beta, M, D, eps, (bf16*)y16, ldy16, y32, ldy32, mean, rstd, act)))
     default: CB_CHECK_ARG(false, "layernorm: unsupported D=%d", D);
   }
   CB_LAUNCH_CHECK();
@@ -553,10 +558,10 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
 #define LN_BWD_SMALL(L)                                                                                             \
   do {                                                                                                              \
     if (bf)                                                                                                         \
-      ln_bwd_small_kernel<L, UNR, true><<<sb, 256, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
+      cb_launch(ln_bwd_small_kernel<L, UNR, true>, sb, 256, 0, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
                                                            lddx32, (bf16*)dx16, lddx16, dgamma, dbeta, dxsum, beta_act); \
     else                                                                                                            \
-      ln_bwd_small_kernel<L, UNR, false><<<sb, 256, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
+      cb_launch(ln_bwd_small_kernel<L, UNR, false>, sb, 256, 0, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, dx32, \
                                                             lddx32, (bf16*)dx16, lddx16, dgamma, dbeta, dxsum, beta_act); \
   } while (0)
     if (D == 16) LN_BWD_SMALL(4);
@@ -586,7 +591,7 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
       CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
       configured = smem;                                                                                              \
     }                                                                                                                 \
-    kern<<<blocks, LNB_WARPS * 32, smem, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, D, dx32, lddx32,  \
+    cb_launch(kern, blocks, LNB_WARPS * 32, smem, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, D, dx32, lddx32,  \
                                               (bf16*)dx16, lddx16, dgamma, dbeta, dxsum, beta_act, stages, slot_bytes); \
   } while (0)
       switch (nv) {
@@ -609,7 +614,7 @@ extern "C" int cb_layernorm_bwd(const void* dy, long long lddy, int dy_dtype, co
   const int blocks = (int)min((long long)(M + 7) / 8, (long long)cb_sm_count() * 2);
   const size_t smem = 2 * (size_t)D * sizeof(float);
 #define LN_BWD_CALL(BF)                                                                                              \
-  ln_bwd_kernel<NV, BF><<<blocks, 256, smem, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, D, dx32, lddx32, \
+  cb_launch(ln_bwd_kernel<NV, BF>, blocks, 256, smem, s, dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, M, D, dx32, lddx32, \
                                                   (bf16*)dx16, lddx16, dgamma, dbeta, beta_act)
   switch (nv) {
     LN_DISPATCH(1, if (bf) LN_BWD_CALL(true); else LN_BWD_CALL(false))

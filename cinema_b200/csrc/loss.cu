@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict
                                                          const int* __restrict__ slot, const float* __restrict__ pred,
                                                          int n_drop, int norm_target, float eps, float* __restrict__ acc,
                                                          float* __restrict__ diff) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int E = g.P * g.C;
@@ -146,6 +147,7 @@ struct FinalizeArgs {
 // d loss / d pred scale of every view.
 __global__ void mae_loss_finalize_kernel(const float* __restrict__ acc, FinalizeArgs a, float* __restrict__ out,
                                          float* __restrict__ scales) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float sum = 0.f;
   int n_fin = 0;
@@ -175,7 +177,7 @@ extern "C" int cb_mae_loss_finalize(const float* acc, int n_views, const float* 
   a.V = n_views;
   for (int v = 0; v < 8; ++v) a.sq_count[v] = a.patch_count[v] = 1.f;
   for (int v = 0; v < n_views; ++v) a.sq_count[v] = sq_count[v], a.patch_count[v] = patch_count[v];
-  mae_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, a, out, scales);
+  cb_launch(mae_loss_finalize_kernel, 1, 32, 0, (cudaStream_t)stream, acc, a, out, scales);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -200,7 +202,7 @@ extern "C" int cb_masked_mse_fwd(const float* image, int B, int C, int ndim, con
   const long long total = (long long)B * g.n_tok;
   if (total <= 0) return 0;
   const int blocks = (int)min((total + 7) / 8, (long long)cb_sm_count() * 8);
-  masked_mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(image, g, B, mask, slot, pred, n_drop, norm_target, eps,
+  cb_launch(masked_mse_kernel, blocks, 256, 0, (cudaStream_t)stream, image, g, B, mask, slot, pred, n_drop, norm_target, eps,
                                                               acc, diff);
   CB_LAUNCH_CHECK();
   return 0;

@@ -10,6 +10,7 @@
 namespace {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   float acc = 0.f;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, long long n, const float* __restrict__ hyper, float beta1, float beta2, float eps,
              float wd, const float* __restrict__ gnorm_sq, float max_norm, float grad_scale) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2 = __ldg(hyper + 2);
   float gs = grad_scale;
   if (gnorm_sq != nullptr) {
@@ -84,7 +86,7 @@ inline int grid_for(long long n4) {
 extern "C" int cb_sumsq_f32(const float* x, long long n, float* out, void* stream) {
   if (n <= 0) return 0;
   CB_CHECK_ARG(((uintptr_t)x & 15) == 0, "sumsq: buffer must be 16-byte aligned");
-  sumsq_kernel<<<grid_for(n >> 2), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  cb_launch(sumsq_kernel, grid_for(n >> 2), 256, 0, (cudaStream_t)stream, x, n, out);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -96,7 +98,7 @@ extern "C" int cb_adamw_flat(float* p, const float* g, float* m, float* v, void*
   CB_CHECK_ARG(n % 4 == 0, "adamw: segment length %lld must be a multiple of 4", n);
   CB_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p16 & 7) == 0,
                "adamw: buffers must be 16-byte aligned");
-  adamw_kernel<<<grid_for(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p16, n, hyper, beta1, beta2, eps,
+  cb_launch(adamw_kernel, grid_for(n >> 2), 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)p16, n, hyper, beta1, beta2, eps,
                                                                   weight_decay, gnorm_sq, max_norm, grad_scale);
   CB_LAUNCH_CHECK();
   return 0;

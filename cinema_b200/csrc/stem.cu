@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256)
 dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const bf16* __restrict__ w,
               const float* __restrict__ bias, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
               const int* __restrict__ keep, DwGeom g, int flip) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* wsm = reinterpret_cast<bf16*>(smem);                 // [taps][C]
   bf16* tile = wsm + (size_t)g.taps * g.C;                   // [R][C]
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256)
 dwconv_wgrad_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dy, float* __restrict__ dw,
                     float* __restrict__ db, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
                     const int* __restrict__ keep, DwGeom g) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* tile = reinterpret_cast<bf16*>(smem);                // [R][C]
   bf16* dys = tile + (size_t)g.R * g.C;                      // [P][C]
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(128, 4)  // <= 128 registers: 16 warps per SM 
 dwconv_fast_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const bf16* __restrict__ w,
                    const float* __restrict__ bias, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
                    const int* __restrict__ keep, DwGeom g, int flip) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   using T = Fast<F>;
   constexpr int E2 = ND == 3 ? KS : 1;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(320)
 dwconv_wgrad_fast_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dy, float* __restrict__ dw,
                          float* __restrict__ db, const unsigned char* __restrict__ mask, const int* __restrict__ slot,
                          const int* __restrict__ keep, DwGeom g) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   using T = Fast<F>;
   constexpr int E2 = ND == 3 ? KS : 1;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -409,7 +413,7 @@ int launch_fast_fwd(const void* in, void* out, const void* w, const float* bias,
   long long blocks = (tasks + 3) / 4;
   const long long cap = (long long)cb_sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, 128, smem, stream>>>((const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot, keep, g,
+  cb_launch(kern, (unsigned)blocks, 128, smem, stream, (const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot, keep, g,
                                                transpose);
   CB_LAUNCH_CHECK();
   return 0;
@@ -434,13 +438,14 @@ int launch_fast_wgrad(const void* in, const void* dy, float* dw, float* db, cons
   long long blocks = (items + spb - 1) / spb;
   const long long cap = (long long)cb_sm_count() * 2;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>((const bf16*)in, (const bf16*)dy, dw, db, mask, slot, keep, g);
+  cb_launch(kern, (unsigned)blocks, warps * 32, smem, stream, (const bf16*)in, (const bf16*)dy, dw, db, mask, slot, keep, g);
   CB_LAUNCH_CHECK();
   return 0;
 }
 
 // out[b, i*P + p] = flattened position id, in the level grid (gt * f), of position p of visible token keep[b, i]
 __global__ void expand_index_kernel(const int* __restrict__ keep, long long n_items, DwGeom g, int* __restrict__ out) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_items * g.P) return;
   const long long item = e / g.P;
@@ -476,7 +481,7 @@ extern "C" int cb_expand_token_index(const int* keep, int B, int nk, int ndim, c
   if (int rc = fill(g, B, nk, 8, ndim, grid_tok, f)) return rc;
   const long long total = (long long)B * nk * g.P;
   if (total <= 0) return 0;
-  expand_index_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keep, (long long)B * nk, g, out);
+  cb_launch(expand_index_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, keep, (long long)B * nk, g, out);
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -504,7 +509,7 @@ extern "C" int cb_dwconv_tokens(const void* in, void* out, const void* w, const 
   }
   const long long items = (long long)B * nk;
   const int blocks = (int)(items < (long long)cb_sm_count() * 4 ? items : (long long)cb_sm_count() * 4);
-  dwconv_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot,
+  cb_launch(dwconv_kernel, blocks, 256, smem, (cudaStream_t)stream, (const bf16*)in, (bf16*)out, (const bf16*)w, bias, mask, slot,
                                                             keep, g, transpose);
   CB_LAUNCH_CHECK();
   return 0;
@@ -539,7 +544,7 @@ extern "C" int cb_dwconv_tokens_wgrad(const void* in, const void* dy, float* dw,
   }
   const long long items = (long long)B * nk;
   const int blocks = (int)(items < (long long)cb_sm_count() * 2 ? items : (long long)cb_sm_count() * 2);
-  dwconv_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>((const bf16*)in, (const bf16*)dy, dw, db, mask, slot,
+  cb_launch(dwconv_wgrad_kernel, blocks, 256, smem, (cudaStream_t)stream, (const bf16*)in, (const bf16*)dy, dw, db, mask, slot,
                                                                   keep, g);
   CB_LAUNCH_CHECK();
   return 0;
