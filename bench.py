@@ -170,6 +170,7 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
     from cinema_b200 import _C
 
     records: list[tuple[str, float, torch.cuda.Event, torch.cuda.Event]] = []
+    shapes: list = []
     originals = {}
 
     def flops_of(name, args, kwargs) -> float:
@@ -193,7 +194,15 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
             s.record()
             r = fn(*args, **kwargs)
             e.record()
-            records.append((name, flops_of(name, args, kwargs), s, e))
+            tag = name
+            if name == "gemm":
+                a_, b_ = args[0], args[1]
+                m_, k_ = (a_.shape[1], a_.shape[0]) if kwargs.get("a_mn") else (a_.shape[0], a_.shape[1])
+                n_ = b_.shape[1] if kwargs.get("b_mn") else b_.shape[0]
+                shapes.append((f"M{m_} N{n_} K{k_} a_mn={int(bool(kwargs.get('a_mn')))} b_mn={int(bool(kwargs.get('b_mn')))} "
+                               f"epi={kwargs.get('epilogue', 0)} res={int(kwargs.get('residual') is not None)}", s, e,
+                               2.0 * m_ * n_ * k_))
+            records.append((tag, flops_of(name, args, kwargs), s, e))
             return r
 
         setattr(_C, name, timed)
@@ -207,6 +216,7 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
     for n in names:
         wrap(n)
     engine.VIEW_STREAMS_ENABLED = False  # one stream: every kernel's event pair brackets that kernel alone
+    pdl_was = _C.set_pdl(False)          # and no prologue overlap with the predecessor
     try:
         s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -219,6 +229,7 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
         torch.cuda.synchronize()
     finally:
         engine.VIEW_STREAMS_ENABLED = True
+        _C.set_pdl(pdl_was)
         for n, fn in originals.items():
             setattr(_C, n, fn)
     agg: dict[str, list[float]] = {}
@@ -229,8 +240,17 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
         a[2] += 1
     total = s_all.elapsed_time(e_all)
     own = sum(a[0] for a in agg.values())
+    by_shape: dict[str, list[float]] = {}
+    for tag, s, e, fl in shapes:
+        a = by_shape.setdefault(tag, [0.0, 0.0, 0])
+        a[0] += s.elapsed_time(e)
+        a[1] += fl
+        a[2] += 1
+    top_shapes = [{"gemm": k, "launches": v[2], "ms": round(v[0], 3), "tflops": round(v[1] / v[0] / 1e9, 1)}
+                  for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:24]]
     return {"step_ms": total, "own_kernels_ms": own, "torch_and_gaps_ms": total - own,
             "note": "one eager step on a single stream, launches queued behind a GPU-side sleep; CUDA events per C-ABI launch",
+            "gemm_top_shapes": top_shapes,
             "kernels": {k: {"ms": round(v[0], 3), "launches": v[2], "tflops": round(v[1] / v[0] / 1e9, 1) if v[0] > 0 and v[1] else None}
                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}}
 

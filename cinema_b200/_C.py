@@ -31,6 +31,7 @@ _SIGNATURES = {
     "cb_version": (c_int, []),
     "cb_last_error": (c_char_p, []),
     "cb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cb_set_pdl": (c_int, [c_int]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p]),
@@ -127,6 +128,11 @@ def _row_major_2d(t: torch.Tensor, name: str) -> int:
     if t.dim() != 2 or t.stride(1) != 1:
         raise RuntimeError(f"{name} must be a 2-D tensor with unit inner stride, got {tuple(t.shape)} {t.stride()}")
     return t.stride(0)
+
+
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch for all kernels (default on); returns the previous setting."""
+    return bool(lib().cb_set_pdl(int(enabled)))
 
 
 def device_info() -> tuple[int, int, int]:

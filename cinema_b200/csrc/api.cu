@@ -104,10 +104,18 @@ int cb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   return cb_make_tmap_nd(out, base, 2, dims, strides, box, swizzle_bytes);
 }
 
+static int g_pdl = -1;  // -1: read CB_PDL on first use
+
 bool cb_pdl_enabled() {
-  static const bool on = [] {
+  if (g_pdl < 0) {
     const char* e = getenv("CB_PDL");
-    return !(e != nullptr && e[0] == '0');
-  }();
-  return on;
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
+extern "C" int cb_set_pdl(int enabled) {
+  const int prev = cb_pdl_enabled() ? 1 : 0;
+  g_pdl = enabled ? 1 : 0;
+  return prev;
 }

@@ -203,6 +203,11 @@ int cb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, long 
                   float beta2, float eps, float weight_decay, const float* gnorm_sq, float max_norm, float grad_scale,
                   void* stream);
 
+/* Programmatic dependent launch (griddepcontrol) for all kernels of the library: on by default (env CB_PDL=0 turns it
+ * off); returns the previous setting.  Per-kernel event timing should switch it off: with it, a kernel's prologue runs
+ * in the tail of its predecessor. */
+int cb_set_pdl(int enabled);
+
 #ifdef __cplusplus
 }
 #endif
