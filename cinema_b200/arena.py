@@ -45,18 +45,24 @@ class ParamArena:
             raise ValueError("cinema_b200 keeps fp32 master parameters (reference state-dict contract)")
 
         names = {id(p): n for n, p in root.named_parameters()}
-        order: list[list[nn.Parameter]] = []
         placed: set[int] = set()
+        group_of: dict[int, list[nn.Parameter]] = {}  # first member -> group
         for g in groups:
             g = [p for p in g if id(p) in seen]
             if len(g) < 2 or any(id(p) in placed for p in g) or any(p.numel() % 8 for p in g[:-1]):
                 continue  # cannot be laid out back to back with 16-byte aligned members; callers re-check adjacency
             if len({self.category(p, names[id(p)]) for p in g}) != 1:
                 continue
-            order.append(g)
+            group_of[id(g[0])] = g
             placed.update(id(p) for p in g)
+        # registration order, a fusion group sitting where its first member is registered: the parameters of a module
+        # subtree then occupy ONE flat range per optimiser category, which is what the bucketed gradient all-reduce
+        # (train.py) hands to NCCL as soon as that subtree's backward is done
+        order: list[list[nn.Parameter]] = []
         for p in params:
-            if id(p) not in placed:
+            if id(p) in group_of:
+                order.append(group_of[id(p)])
+            elif id(p) not in placed:
                 order.append([p])
         # optimiser regions: [weight-decayed | not decayed | frozen] so that AdamW is a few long flat launches
         order.sort(key=lambda g: self.category(g[0], names[id(g[0])]))
@@ -104,6 +110,24 @@ class ParamArena:
         if not p.requires_grad:
             return 2
         return 1 if (p.ndim <= 1 or name.endswith(".bias")) else 0
+
+    def ranges_of(self, params: Iterable[nn.Parameter]) -> list[tuple[int, int]]:
+        """Flat [start, end) ranges (alignment padding included) covering exactly the given trainable parameters:
+        consecutive parameters of the arena are merged, any other parameter in between splits the range."""
+        want = {id(p) for p in params if p.requires_grad}
+        layout = sorted(((self._off[id(p)], p) for p in self.params), key=lambda t: t[0])
+        out: list[list[int]] = []
+        open_run = False
+        for off, p in layout:
+            if id(p) in want:
+                if open_run:
+                    out[-1][1] = off + p.numel()
+                else:
+                    out.append([off, off + p.numel()])
+                    open_run = True
+            else:
+                open_run = False
+        return [(a, b) for a, b in out]
 
     def segments(self) -> list[tuple[int, int, int]]:
         """Maximal runs (start, end, category) of the arena under the CURRENT requires_grad flags."""

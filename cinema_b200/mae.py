@@ -256,6 +256,8 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
         dx32, dx16 = engine.block_bwd(dx32, dx16, ew[j], b, st.enc_saved[j], None, None,
                                       fc2_bias_done=gb_of(j) is not None, out_bias=gb_of(j - 1))
         st.enc_saved[j] = None
+        if j == len(ew) // 2 and j > 0:
+            _grad_stage_done(model, "encoder_hi")  # encoder.norm and blocks[depth // 2:] are final
     dx0 = dx32.view(b, n, d)
     cls = model.encoder.cls_token
     if cls.requires_grad:
@@ -273,6 +275,25 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
                 _C.scatter_patches(dp, tgt[0], tgt[1], ps, tgt[2], True, accumulate=True)
     return vs
 
+
+
+def _grad_stage_done(model, stage: str) -> None:
+    """Tell a data-parallel trainer that the gradients of a module subtree are final, so that their all-reduce can
+    start while the rest of the backward still runs (``MAETrainer`` installs ``model._grad_stage_hook``)."""
+    hook = getattr(model, "_grad_stage_hook", None)
+    if hook is not None:
+        hook(stage)
+
+
+def grad_stages(model) -> dict[str, list[nn.Parameter]]:
+    """Parameter sets whose gradients become final at the two points reported by :func:`_grad_stage_done`."""
+    dec = [*model.dec_linear.parameters(), *model.dec_embed_dict.parameters(), *model.decoder.parameters(),
+           *model.pred_head_dict.parameters()]
+    blocks = list(model.encoder.blocks)
+    hi = [*model.encoder.norm.parameters()]
+    for blk in blocks[len(blocks) // 2:]:
+        hi += list(blk.parameters())
+    return {"decoder": dec, "encoder_hi": hi if len(blocks) // 2 > 0 else []}
 
 
 def _needs(flags, counts):
@@ -545,6 +566,7 @@ class _MAEFn(torch.autograd.Function):
             if mt.requires_grad and nm > 0:
                 _C.colsum_seg(dxq, s["qoffs"][i], nm, arena.grad_view(mt).view(-1))
         d_f32 = engine.linear_bwd(dy16, s["f16"], s["w_dl"], dx_dtype=F32)
+        _grad_stage_done(model, "decoder")  # dec_linear, decoder, decoder embeddings and prediction heads are final
         targets, dskips = _build_targets(views, s["sources"], s["stems"], s["skips"], s["needs"])
         vs = _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets)
         for i, stem_state in enumerate(s["stems"]):

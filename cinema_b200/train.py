@@ -5,7 +5,8 @@
   ------------------------------------------------  -------------------------------------------------
   batch.to(device) per view                         pinned host buffers -> static device buffers (async)
   autocast forward + autograd backward (~4k nodes)  one fused autograd node, replayed as a CUDA graph
-  DDP reducer, 25 MB fp32 buckets, every micro-step ONE NCCL all-reduce of the flat gradient arena
+  DDP reducer, 25 MB fp32 buckets, every micro-step flat gradient arena, 3 buckets (decoder / upper encoder / rest)
+                                                    all-reduced by NCCL while the backward still runs
   GradScaler.unscale_ + clip_grad_norm_ + AdamW     sum-of-squares kernel + one fused AdamW kernel per
   (~10 passes over ~600 tensors)                    arena region (clip folded in, bf16 shadow refreshed)
   metrics .item() x 14 (host syncs)                 loss copied to pinned memory, read one step later
@@ -79,7 +80,7 @@ class MAETrainer:
 
     def __init__(self, model: nn.Module, *, lr: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.05,
                  clip_grad: float | None = 5.0, enc_mask_ratio: float = 0.75, use_cuda_graph: bool = True,
-                 process_group=None, graph_warmup: int = 2) -> None:
+                 process_group=None, graph_warmup: int = 2, overlap_allreduce: bool | None = None) -> None:
         self.model = model
         self.ratio = enc_mask_ratio
         self.pg = process_group
@@ -94,6 +95,28 @@ class MAETrainer:
         self.arena.gflat.zero_()
         self.arena.prepare_grads()
         self.opt = FlatAdamW(self.arena, lr, betas, 1e-8, weight_decay, clip_grad)
+        # Bucketed gradient all-reduce overlapped with the backward pass: the model reports when the decoder subtree and
+        # the upper half of the encoder are final (mae._grad_stage_done); their flat ranges go to NCCL asynchronously
+        # while the rest of the backward runs, the remainder follows after the backward.  All of it is inside the
+        # forward/backward region, so it is captured in the CUDA graph together with the kernels.
+        self._stage_ranges: dict[str, list[tuple[int, int]]] = {}
+        self._rest_ranges: list[tuple[int, int]] = [(0, self.arena.numel)]
+        self._pending: list = []
+        if overlap_allreduce is None:  # opt-in for now (CB_OVERLAP_ALLREDUCE=1): see DESIGN.md section 7
+            import os
+
+            overlap_allreduce = os.environ.get("CB_OVERLAP_ALLREDUCE", "0") == "1"
+        self.overlap = self.world > 1 and overlap_allreduce and hasattr(model, "dec_linear")
+        if self.overlap:
+            from cinema_b200.mae import grad_stages
+
+            covered: list[nn.Parameter] = []
+            for name, params in grad_stages(model).items():
+                self._stage_ranges[name] = self.arena.ranges_of(params)
+                covered += [p for p in params if p.requires_grad]
+            ids = {id(p) for p in covered}
+            self._rest_ranges = self.arena.ranges_of([p for p in self.arena.params if id(p) not in ids])
+            model._grad_stage_hook = self._on_stage
         self.use_graph = use_cuda_graph and self.arena.device.type == "cuda"
         self.graph_warmup = graph_warmup
         self._n_calls = 0
@@ -119,14 +142,25 @@ class MAETrainer:
         for k, v in batch.items():
             self._inputs[k].copy_(v, non_blocking=True)
 
+    def _on_stage(self, stage: str) -> None:
+        for s, e in self._stage_ranges.get(stage, ()):
+            self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
     def _fwd_bwd(self) -> None:
         self.arena.gflat.zero_()
+        self._pending = []
         loss, _, _, _ = self.model(self._inputs, self.ratio)
         loss.backward()
         self._loss = loss.detach()
+        if self.overlap:  # the rest of the arena, then join every bucket before the optimiser reads the gradients
+            for s, e in self._rest_ranges:
+                self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            for w in self._pending:
+                w.wait()
+            self._pending = []
 
     def _reduce(self) -> None:
-        if self.world > 1:
+        if self.world > 1 and not self.overlap:
             dist.all_reduce(self.arena.gflat, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _opt_apply(self) -> None:

@@ -33,7 +33,7 @@ def _one_step(images, masks, world):
     model = CineMA(**g["kw"])
     model.load_state_dict(g["state_dict"])
     model.train()
-    tr = MAETrainer(model, lr=1e-3, use_cuda_graph=False)
+    tr = MAETrainer(model, lr=1e-3, use_cuda_graph=False, overlap_allreduce=True)  # bucketed path (no-op at world 1)
     # fixed masks so that both layouts see the same problem
     orig = model.forward
     model.forward = lambda image_dict, ratio: orig(image_dict, ratio, enc_mask_dict=masks)
@@ -84,3 +84,29 @@ def g_flat_initial(g):
     model = CineMA(**g["kw"])
     model.load_state_dict(g["state_dict"])
     return ensure_arena(model).flat32.clone()
+
+
+def test_allreduce_buckets_partition_the_arena():
+    """The overlapped all-reduce sends three buckets (decoder subtree, upper encoder half, rest): their flat ranges must
+    be disjoint and cover every trainable parameter exactly once."""
+    _patch()
+    from cinema_b200 import CineMA
+    from cinema_b200.arena import ensure_arena
+    from cinema_b200.mae import grad_stages
+
+    g = torch.load(GOLDEN)
+    model = CineMA(**g["kw"])
+    arena = ensure_arena(model)
+    stages = grad_stages(model)
+    covered = {id(p) for ps in stages.values() for p in ps}
+    ranges = [r for ps in stages.values() for r in arena.ranges_of(ps)]
+    ranges += arena.ranges_of([p for p in arena.params if id(p) not in covered])
+    hit = torch.zeros(arena.numel, dtype=torch.int32)
+    for s, e in ranges:
+        hit[s:e] += 1
+    assert int(hit.max()) == 1, "buckets overlap"
+    for p in arena.params:
+        off = arena._off[id(p)]
+        assert bool((hit[off:off + p.numel()] == (1 if p.requires_grad else 0)).all()), arena._names[id(p)]
+    # a module subtree is a handful of contiguous runs (one per optimiser category, registration-order layout)
+    assert len(arena.ranges_of(stages["decoder"])) <= 3
