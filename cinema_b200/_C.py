@@ -34,7 +34,7 @@ _SIGNATURES = {
     "cb_set_pdl": (c_int, [c_int]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
-                             c_longlong, c_int, c_float, c_int, c_int, c_void_p]),
+                             c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
     "cb_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
     "cb_attention_fwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 4
                          + [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -145,8 +145,9 @@ def device_info() -> tuple[int, int, int]:
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bool = False, b_mn: bool = False,
          accumulate: bool = False, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, aux: torch.Tensor | None = None, epilogue: int = EPI_NONE,
-         alpha: float = 1.0, split_k: int = 0, block_n: int = 0) -> None:
-    """C[M,N] = alpha * A . B^T with the fused epilogue of cb_gemm_bf16 (see include/cinema_b200.h)."""
+         alpha: float = 1.0, split_k: int = 0, block_n: int = 0, colsum: torch.Tensor | None = None) -> None:
+    """C[M,N] = alpha * A . B^T with the fused epilogue of cb_gemm_bf16 (see include/cinema_b200.h).
+    ``colsum`` (fp32 (N,), optional, bf16 outputs): += column sums of the stored bf16 values."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb = _row_major_2d(a, "A"), _row_major_2d(b, "B")
     m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -173,9 +174,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bo
         assert aux.dtype == torch.bfloat16 and tuple(aux.shape) == (m, n)
     if out2 is not None:
         assert out2.dtype == torch.bfloat16
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == n and colsum.is_contiguous()
     _check(lib().cb_gemm_bf16(_ptr(a), lda, int(a_mn), _ptr(b), ldb, int(b_mn), m, n, k, _ptr(out), ldo, out_dt,
                               int(accumulate), _ptr(out2), ldo2, _ptr(bias), _ptr(residual), ldr, _ptr(aux), ldaux,
-                              epilogue, float(alpha), split_k, block_n, _stream()), "gemm")
+                              epilogue, float(alpha), split_k, block_n, _ptr(colsum), _stream()), "gemm")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:

@@ -43,6 +43,7 @@ struct GemmArgs {
   long long ldaux;
   int epi;
   float alpha;
+  float* colsum;  // optional: column sums of the bf16 output (bias gradient of the consumer)
 };
 
 // CTAS == 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2; each
@@ -309,10 +310,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 4; ++i) res[i] = pre_res[i], aux[i] = pre_aux[i];
         if ((MODE == 2 || ((MODE == 0 || MODE == 3) && has_res)) && c + 1 < CHUNKS) prefetch(c + 1);
-        if (!col_ok) continue;  // warp-uniform per 16-byte column group only when N % 16 != 0; harmless otherwise
+        const bool want_cs = (MODE == 0 || MODE == 2) && p.colsum != nullptr;
+        if (!col_ok && !want_cs) continue;  // (with colsum every lane stays for the shuffles below)
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (!((vmask >> i) & 1u)) continue;
+          if (!((vmask >> i) & 1u) || !col_ok) continue;
           float* v = x[i];
           v[0] = fmaf(v[0], p.alpha, bias4.x), v[1] = fmaf(v[1], p.alpha, bias4.y);
           v[2] = fmaf(v[2], p.alpha, bias4.z), v[3] = fmaf(v[3], p.alpha, bias4.w);
@@ -328,7 +331,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const float2 a0 = unpack_bf16(aux[i].x), a1 = unpack_bf16(aux[i].y);
             v[0] *= gelu_grad_fast(a0.x), v[1] *= gelu_grad_fast(a0.y);
             v[2] *= gelu_grad_fast(a1.x), v[3] *= gelu_grad_fast(a1.y);
-            *reinterpret_cast<uint2*>(out16 + eo) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            const uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            *reinterpret_cast<uint2*>(out16 + eo) = pk;
+            if (want_cs) {
+              const float2 c0 = unpack_bf16(pk.x), c1 = unpack_bf16(pk.y);
+              cs[0] += c0.x, cs[1] += c0.y, cs[2] += c1.x, cs[3] += c1.y;
+            }
           } else if constexpr (MODE == 4) {
             red_add_v4(out32 + eo, v[0], v[1], v[2], v[3]);
           } else {
@@ -340,8 +348,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             } else {
               *reinterpret_cast<uint2*>(out16 + eo) = pk;
               if (has_out2) *reinterpret_cast<uint2*>(p.out2 + (o2 + i * s28 + c * 16)) = pk;
+              if (want_cs) {
+                const float2 c0 = unpack_bf16(pk.x), c1 = unpack_bf16(pk.y);
+                cs[0] += c0.x, cs[1] += c0.y, cs[2] += c1.x, cs[3] += c1.y;
+              }
             }
           }
+        }
+        if (want_cs) {  // 32 rows x 4 columns per lane quad: reduce over the eight row groups, one red.v4 per quad
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], o);
+          }
+          if (sub == 0 && col_ok) red_add_v4(p.colsum + col, cs[0], cs[1], cs[2], cs[3]);
         }
       }
       tcgen05_fence_before();
@@ -435,7 +455,7 @@ int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void*
 extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                             int M, int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2,
                             long long ldo2, const float* bias, const float* residual, long long ldr, const void* aux,
-                            long long ldaux, int epilogue, float alpha, int split_k, int block_n, void* stream) {
+                            long long ldaux, int epilogue, float alpha, int split_k, int block_n, float* colsum, void* stream) {
   CB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CB_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   CB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B TMA pitch)");
@@ -463,7 +483,10 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
   p.out2 = reinterpret_cast<bf16*>(out2), p.ldo2 = ldo2;
   p.bias = bias, p.residual = residual, p.ldr = ldr;
   p.aux = reinterpret_cast<const bf16*>(aux), p.ldaux = ldaux;
-  p.epi = epilogue, p.alpha = alpha;
+  p.epi = epilogue, p.alpha = alpha, p.colsum = colsum;
+  CB_CHECK_ARG(colsum == nullptr || (out_dtype == CB_DT_BF16 && epilogue != CB_EPI_GELU && !accumulate),
+               "gemm: colsum needs a bf16 output without the GELU epilogue");
+  CB_CHECK_ARG(((uintptr_t)colsum & 15) == 0, "gemm: colsum must be 16-byte aligned");
   p.num_m_tiles = (M + BM - 1) / BM;
 
   const int sms = cb_sm_count();

@@ -98,10 +98,13 @@ def linear_gelu_fwd(x16: torch.Tensor, w: LinW) -> tuple[torch.Tensor, torch.Ten
 
 def linear_bwd(dy16: torch.Tensor, x16: torch.Tensor | None, w: LinW, *, need_dx: bool = True,
                gelu_aux: torch.Tensor | None = None, dx_dtype: torch.dtype = BF16,
-               dx_out: torch.Tensor | None = None, bias_done: bool = False) -> torch.Tensor | None:
+               dx_out: torch.Tensor | None = None, bias_done: bool = False,
+               dx_colsum: torch.Tensor | None = None) -> torch.Tensor | None:
     """dW += dy^T x, db += colsum(dy), and dx = dy W (optionally * GELU'(gelu_aux), the input's pre-activation).
     ``bias_done``: the kernel that produced ``dy16`` already accumulated its column sums into ``w.gb``
-    (``ln_bwd(..., dxsum=w.gb)``)."""
+    (``ln_bwd(..., dxsum=w.gb)`` or an upstream ``linear_bwd(..., dx_colsum=w.gb)``).
+    ``dx_colsum``: fp32 (K,) buffer that receives the column sums of the bf16 dx written here -- the bias gradient of
+    the Linear layer that produced this layer's input (fused into the dgrad GEMM epilogue)."""
     if w.gw is not None:
         _C.gemm(dy16, x16, w.gw, a_mn=True, b_mn=True, accumulate=True)
     if w.gb is not None and not bias_done:
@@ -110,10 +113,12 @@ def linear_bwd(dy16: torch.Tensor, x16: torch.Tensor | None, w: LinW, *, need_dx
         return None
     if dx_out is None:
         dx_out = torch.empty((dy16.shape[0], w.k), dtype=dx_dtype, device=dy16.device)
+    if dx_colsum is not None and dx_out.dtype != BF16:
+        raise ValueError("dx_colsum needs a bf16 dx")
     if gelu_aux is not None:
-        _C.gemm(dy16, w.w16, dx_out, b_mn=True, aux=gelu_aux, epilogue=_C.EPI_GELU_BWD)
+        _C.gemm(dy16, w.w16, dx_out, b_mn=True, aux=gelu_aux, epilogue=_C.EPI_GELU_BWD, colsum=dx_colsum)
     else:
-        _C.gemm(dy16, w.w16, dx_out, b_mn=True)
+        _C.gemm(dy16, w.w16, dx_out, b_mn=True, colsum=dx_colsum)
     return dx_out
 
 
@@ -282,8 +287,8 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
     n = m // b
     hd = d // w.n_heads
     # ---- MLP path
-    dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done)
-    dh2 = linear_bwd(dpre, h2, w.fc1)
+    dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done, dx_colsum=w.fc1.gb)
+    dh2 = linear_bwd(dpre, h2, w.fc1, bias_done=w.fc1.gb is not None)
     proj_gb = fusable_bias(w.proj, d)
     dx32, dx16 = ln_bwd(dh2, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32, dxsum=proj_gb)
     # ---- attention path

@@ -109,8 +109,8 @@ def _block_bwd(dx32, dx16, w: ConvBlockW, geo: Geometry, f, saved, fc2_bias_done
     """``fc2_bias_done`` / ``out_bias``: bias gradients fused into the producing LayerNorm backward (engine.block_bwd)."""
     x, mean1, rstd1, h, h1, h2, x1, mean2, rstd2, g, pre, act = saved
     c = x.shape[1]
-    dpre = engine.linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done)
-    dg = engine.linear_bwd(dpre, g, w.fc1)
+    dpre = engine.linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done, dx_colsum=w.fc1.gb)
+    dg = engine.linear_bwd(dpre, g, w.fc1, bias_done=w.fc1.gb is not None)
     conv2_gb = engine.fusable_bias(w.conv2, c)
     dx32, dx16 = engine.ln_bwd(dg, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32, dxsum=conv2_gb)
     dh2 = engine.linear_bwd(dx16, h2, w.conv2, bias_done=conv2_gb is not None)

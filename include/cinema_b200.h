@@ -41,6 +41,8 @@ int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (fp32); store to out as bf16 / fp32, or red.add into fp32 out when accumulate=1; out2 (if
  * given, non-GELU) receives a bf16 copy of the stored value.
  * split_k: 0 = auto (only ever >1 when accumulate=1).  block_n: 0 = auto, or 64/128/256.
+ * colsum (fp32 [N], may be NULL; bf16-output epilogues without GELU only): colsum[n] += sum_m of the bf16 values stored to
+ * out -- the bias gradient of the Linear layer that consumes `out` as its output gradient (no separate column-sum pass).
  * Replaces nn.Linear forward/backward: cinema/vit.py:472-477,498-499,520 (q, kv, proj),
  * timm Mlp fc1/GELU/fc2 (cinema/vit.py:570-575), cinema/vit.py:294-298,342 (PatchEmbed.proj),
  * cinema/convvit.py:121,205 (linear), cinema/convvit.py:252,284 (k==s down convs as GEMM),
@@ -48,7 +50,7 @@ int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
                  int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2, long long ldo2,
                  const float* bias, const float* residual, long long ldr, const void* aux, long long ldaux,
-                 int epilogue, float alpha, int split_k, int block_n, void* stream);
+                 int epilogue, float alpha, int split_k, int block_n, float* colsum, void* stream);
 
 /* column sums of a bf16 [M,N] matrix accumulated (atomically) into fp32 out[N]: bias gradients.
  * Replaces the reduce kernels autograd runs for nn.Linear bias (same call sites as above). */

@@ -29,7 +29,7 @@ def _gelu_grad(x):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, accumulate=False, out2=None, bias=None, residual=None, aux=None,
-         epilogue=EPI_NONE, alpha=1.0, split_k=0, block_n=0):
+         epilogue=EPI_NONE, alpha=1.0, split_k=0, block_n=0, colsum=None):
     assert a.dtype == BF16 and b.dtype == BF16
     am = a.float().t() if a_mn else a.float()
     bm = b.float() if b_mn else b.float().t()  # (K, N)
@@ -51,6 +51,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, accumulate=False, out2=None, bias
         out.add_(acc)
     else:
         out.copy_(acc.to(out.dtype))
+    if colsum is not None:
+        assert out.dtype == BF16 and epilogue != EPI_GELU
+        colsum.add_(acc.to(BF16).float().sum(0))
     if out2 is not None:
         out2.copy_(acc.to(BF16))
 

@@ -470,3 +470,27 @@ def test_layernorm_gelu_fwd_bwd(m, d):
     torch.testing.assert_close(dx, xr.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(dg, gr.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(dbt, br.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 512, 256), (333, 72, 64), (4200, 3072, 768)])
+def test_gemm_epilogue_column_sums(m, n, k):
+    """colsum: the bias gradient of the consumer layer, fused into the dgrad epilogue (plain and GELU' flavours); it must
+    equal a separate column sum over the stored bf16 output."""
+    dy = bf16_randn(m, k, seed=1)
+    w = bf16_randn(k, n, scale=0.05, seed=2)  # [K, N]: read MN-major like a dgrad
+    aux = bf16_randn(m, n, seed=3)
+    for use_aux in (False, True):
+        out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+        cs = torch.zeros(n, device=DEV)
+        if use_aux:
+            _C.gemm(dy, w, out, b_mn=True, aux=aux, epilogue=_C.EPI_GELU_BWD, colsum=cs)
+        else:
+            _C.gemm(dy, w, out, b_mn=True, colsum=cs)
+        ref = out.float().sum(0)
+        torch.testing.assert_close(cs, ref, rtol=2e-4, atol=2e-3 * float(out.float().abs().max()) + 1e-3)
+        out2 = torch.empty_like(out)
+        if use_aux:
+            _C.gemm(dy, w, out2, b_mn=True, aux=aux, epilogue=_C.EPI_GELU_BWD)
+        else:
+            _C.gemm(dy, w, out2, b_mn=True)
+        assert torch.equal(out, out2)  # the side output does not change the main one
