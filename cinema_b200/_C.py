@@ -34,7 +34,7 @@ _SIGNATURES = {
     "cb_set_pdl": (c_int, [c_int]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
-                             c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
+                             c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "cb_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
     "cb_attention_fwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 4
                          + [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -60,7 +60,7 @@ _SIGNATURES = {
     "cb_embed_rows_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]),
     "cb_colsum_seg_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "cb_scale_cast_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_void_p]),
+    "cb_scale_cast_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_longlong, c_void_p]),
     "cb_sumsq_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "cb_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_float, c_float,
                               c_float, c_float, c_void_p, c_float, c_float, c_void_p]),
@@ -145,9 +145,11 @@ def device_info() -> tuple[int, int, int]:
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bool = False, b_mn: bool = False,
          accumulate: bool = False, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, aux: torch.Tensor | None = None, epilogue: int = EPI_NONE,
-         alpha: float = 1.0, split_k: int = 0, block_n: int = 0, colsum: torch.Tensor | None = None) -> None:
+         alpha: float = 1.0, split_k: int = 0, block_n: int = 0, colsum: torch.Tensor | None = None,
+         row_scale: torch.Tensor | None = None, rows_per_group: int = 0) -> None:
     """C[M,N] = alpha * A . B^T with the fused epilogue of cb_gemm_bf16 (see include/cinema_b200.h).
-    ``colsum`` (fp32 (N,), optional, bf16 outputs): += column sums of the stored bf16 values."""
+    ``colsum`` (fp32 (N,), optional, bf16 outputs): += column sums of the stored bf16 values.
+    ``row_scale`` (fp32, one factor per ``rows_per_group`` rows): scales alpha * acc + bias before the residual."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb = _row_major_2d(a, "A"), _row_major_2d(b, "B")
     m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
@@ -176,9 +178,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bo
         assert out2.dtype == torch.bfloat16
     if colsum is not None:
         assert colsum.dtype == torch.float32 and colsum.numel() == n and colsum.is_contiguous()
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and rows_per_group > 0
+        assert row_scale.numel() * rows_per_group >= m
     _check(lib().cb_gemm_bf16(_ptr(a), lda, int(a_mn), _ptr(b), ldb, int(b_mn), m, n, k, _ptr(out), ldo, out_dt,
                               int(accumulate), _ptr(out2), ldo2, _ptr(bias), _ptr(residual), ldr, _ptr(aux), ldaux,
-                              epilogue, float(alpha), split_k, block_n, _ptr(colsum), _stream()), "gemm")
+                              epilogue, float(alpha), split_k, block_n, _ptr(colsum), _ptr(row_scale), int(rows_per_group),
+                              _stream()), "gemm")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
@@ -317,14 +323,17 @@ def colsum_seg(x: torch.Tensor, off: int, k: int, out: torch.Tensor) -> None:
            "colsum_seg")
 
 
-def scale_cast(src: torch.Tensor, dst: torch.Tensor, scale_dev: torch.Tensor | None = None, scale: float = 1.0) -> None:
-    """dst (bf16) = src (fp32) * scale * scale_dev[0]."""
+def scale_cast(src: torch.Tensor, dst: torch.Tensor, scale_dev: torch.Tensor | None = None, scale: float = 1.0,
+               group: int = 0) -> None:
+    """dst (bf16) = src (fp32) * scale * scale_dev[0], or * scale_dev[i // group] per element i when ``group`` > 0."""
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
     if scale_dev is not None:
-        assert scale_dev.dtype == torch.float32
-    _check(lib().cb_scale_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _ptr(scale_dev), float(scale), _stream()),
-           "scale_cast")
+        assert scale_dev.dtype == torch.float32 and scale_dev.is_contiguous()
+    if group:
+        assert scale_dev is not None and scale_dev.numel() * group == src.numel()
+    _check(lib().cb_scale_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _ptr(scale_dev), float(scale), int(group),
+                                    _stream()), "scale_cast")
 
 
 def mae_loss_finalize(acc: torch.Tensor, sq_count, patch_count, out: torch.Tensor, scales: torch.Tensor) -> None:

@@ -148,3 +148,315 @@ class MultiScaleFusion(nn.Module):
 
 def n_tokens_of(grid: tuple[int, ...]) -> int:
     return math.prod(grid)
+
+
+# ------------------------------------------------------------------------------------------
+# ConvViT: the classification / regression fine-tuning model on top of the pre-trained encoder
+# ------------------------------------------------------------------------------------------
+class _FeatureFn(torch.autograd.Function):
+    """All-token encoder features {cls, view...} with a hand-written backward: conv stem -> token embedding ->
+    ViT encoder -> multi-scale fusion, the same kernels and bookkeeping as the MAE step (cinema_b200/mae.py) with every
+    token visible.  Inputs after ``anchor`` are the dense (cuDNN) skip maps of the views whose stem does not run natively
+    (``model._dense_levels``); their gradients are returned to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, views, images, anchor, *skips_flat):  # noqa: ARG004 - anchor ties the node to the parameters
+        from cinema_b200 import engine, mae, stem  # noqa: F401 - late import: mae imports this module
+        from cinema_b200.arena import ensure_arena
+
+        train = any(ctx.needs_input_grad)
+        arena = ensure_arena(model)
+        arena.refresh_shadow()
+        if train:
+            arena.prepare_grads()
+        counts = model._dense_levels
+        skips, pos = [], 0
+        for c in counts:
+            skips.append([s.detach() for s in skips_flat[pos:pos + c]])
+            pos += c
+        b, dev = images[0].shape[0], images[0].device
+        imgs32 = [im.detach().to(torch.float32).contiguous() for im in images]
+        grids, keep, n_keeps, masks = [], [], [], []
+        for i, v in enumerate(views):
+            down = model.enc_down_dict[v]
+            grid = tuple(s // p for s, p in zip(images[i].shape[2:], down.eff_patch_size))
+            n = math.prod(grid)
+            grids.append(grid), n_keeps.append(n)
+            keep.append(engine.arange_idx(b, 0, n, dev))  # every token is visible: slot == token id
+            masks.append(torch.zeros((b, n), dtype=torch.bool, device=dev))
+        sources, stems = mae._build_sources(model, arena, views, imgs32, skips, keep, masks, keep, grids, n_keeps, b, train)
+        _, fused, st = mae._encode(model, arena, views, sources, keep, n_keeps, b, train, True)
+        if train:
+            ctx.state = dict(model=model, arena=arena, views=views, st=st, n_keeps=n_keeps, b=b, skips=skips, stems=stems,
+                             sources=sources, needs=mae._needs(ctx.needs_input_grad[4:], counts))
+        return (fused["cls"].clone(), *[fused[v] for v in views])
+
+    @staticmethod
+    def backward(ctx, g_cls, *g_views):
+        from cinema_b200 import mae, stem
+
+        s = ctx.state
+        ctx.state = None
+        model, arena, views, st, n_keeps, b = s["model"], s["arena"], s["views"], s["st"], s["n_keeps"], s["b"]
+        d = st.d
+        d_f32 = torch.empty((b + b * sum(n_keeps), d), dtype=torch.float32, device=g_cls.device)
+        d_f32[:b].copy_(g_cls.reshape(b, d))  # rows: [cls (B) | view 0 (B * n) | ...], the layout of mae._encode
+        for i, g in enumerate(g_views):
+            d_f32[st.foffs[i]:st.foffs[i] + b * n_keeps[i]].copy_(g.reshape(b * n_keeps[i], d))
+        targets, dskips = mae._build_targets(views, s["sources"], s["stems"], s["skips"], s["needs"])
+        vs = mae._encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets)
+        for i, stem_state in enumerate(s["stems"]):
+            if stem_state is not None:
+                levels, geo, saved = stem_state
+                with vs.view(i):
+                    stem.stem_bwd(levels, geo, saved, [t[0] for t in mae._native_grad_buffers(targets[i])])
+        vs.join()
+        return (None, None, None, None, *[g for per_view in dskips for g in per_view])
+
+
+class ConvViT(nn.Module):
+    """Multi-view ConvMAE-stem ViT for classification / regression (cinema/convvit.py:334-614): same constructor,
+    attributes, state-dict keys and outputs.  ``feature_forward`` runs (and differentiates) on the B200 kernels; the
+    prediction heads are whatever ``head_layer`` builds (``nn.Linear`` by default), applied to token means in fp32."""
+
+    def __init__(self, image_size_dict, in_chans_dict, n_frames, out_chans, enc_patch_size_dict, enc_scale_factor_dict,
+                 enc_conv_chans, enc_conv_n_blocks, enc_embed_dim, enc_depth, enc_n_heads, mlp_ratio=4, qkv_bias=True,
+                 norm_layer=nn.LayerNorm, norm_eps=1e-5, rotary=False, act_layer=nn.GELU, mlp_layer=None, drop_path=0.0,
+                 norm="layer", head_layer=nn.Linear) -> None:
+        super().__init__()
+        from cinema_b200.vit import Mlp, ViTEncoder
+
+        self.grad_ckpt = False
+        self.native_stem = True  # False: dense cuDNN conv stem (reference evaluation order)
+        self._dense_levels: list[int] = []
+        self.views = list(image_size_dict.keys())
+        self.n_frames = n_frames
+        self.enc_down_dict = nn.ModuleDict({
+            v: DownsampleEncoder(image_size=image_size_dict[v], in_chans=n_frames * in_chans_dict[v],
+                                 patch_size=enc_patch_size_dict[v], scale_factor=enc_scale_factor_dict[v],
+                                 conv_chans=enc_conv_chans, conv_n_blocks=enc_conv_n_blocks, embed_dim=enc_embed_dim, norm=norm)
+            for v in self.views
+        })
+        self.enc_fusion_dict = nn.ModuleDict({
+            v: MultiScaleFusion(image_size=image_size_dict[v], patch_size=enc_patch_size_dict[v],
+                                scale_factor=enc_scale_factor_dict[v], conv_chans=enc_conv_chans, embed_dim=enc_embed_dim,
+                                norm_layer=norm_layer, norm_eps=norm_eps)
+            for v in self.views
+        })
+        self.encoder = ViTEncoder(embed_dim=enc_embed_dim, depth=enc_depth, n_heads=enc_n_heads, mlp_ratio=mlp_ratio,
+                                  qkv_bias=qkv_bias, norm_layer=norm_layer, norm_eps=norm_eps, rotary=rotary,
+                                  act_layer=act_layer, mlp_layer=mlp_layer or Mlp, drop_path=drop_path)
+        self.apply(init_weights)
+        self.pred_head_dict = nn.ModuleDict()  # built after init_weights, like the reference: default torch initialisation
+        if head_layer is not None:
+            for v in [*self.views, "cls"]:
+                self.pred_head_dict[v] = head_layer(enc_embed_dim, out_chans)
+
+    @torch.jit.ignore
+    def set_grad_ckpt(self, enable: bool = True) -> None:
+        """API compatibility (cinema/convvit.py:452-462); nothing is recomputed on the B200 path."""
+        self.grad_ckpt = enable
+        for v in self.views:
+            self.enc_down_dict[v].set_grad_ckpt(enable)
+            self.enc_fusion_dict[v].set_grad_ckpt(enable)
+        self.encoder.set_grad_ckpt(enable)
+        for v in [*self.views, "cls"]:
+            if v in self.pred_head_dict and hasattr(self.pred_head_dict[v], "set_grad_ckpt"):
+                self.pred_head_dict[v].set_grad_ckpt(enable)
+
+    def _backbone_parameters(self):
+        for mod in (self.enc_down_dict, self.enc_fusion_dict, self.encoder):
+            yield from mod.parameters()
+
+    def feature_forward(self, image_dict: dict[str, torch.Tensor],
+                        mask_dict: dict[str, torch.Tensor] | None) -> dict[str, torch.Tensor]:
+        """-> {"cls": (B, 1, D), view: (B, n_patches, D)} fp32 (cinema/convvit.py:464-510).  ``mask_dict`` only hides
+        patches from the depth-wise convolutions of the stem; every token is still embedded and encoded, so with a
+        mask the stem runs densely (cuDNN) and the kernels take over at the token gather."""
+        from cinema_b200 import stem
+
+        views = list(image_dict.keys())
+        if any(v not in self.views for v in views):
+            raise ValueError(f"views {views} must be in self.input_keys {self.views}.")
+        first = image_dict[views[0]]
+        anchor = next((p for p in self._backbone_parameters() if p.requires_grad), None)
+        train = torch.is_grad_enabled() and anchor is not None
+        dense = []
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=first.is_cuda), \
+                torch.set_grad_enabled(train):
+            for v in views:
+                down = self.enc_down_dict[v]
+                if mask_dict is None and self.native_stem and stem.supported(down):
+                    dense.append([])
+                else:
+                    m = None if mask_dict is None else mask_dict[v].to(device=first.device, dtype=torch.bool)
+                    dense.append(down.conv_stem(image_dict[v], m))
+        self._dense_levels = [len(x) for x in dense]
+        flat = [s for per_view in dense for s in per_view]
+        with torch.set_grad_enabled(train):
+            cls, *feats = _FeatureFn.apply(self, views, [image_dict[v] for v in views],
+                                           anchor if train else first.new_zeros(()), *flat)
+        return dict(zip(["cls", *views], [cls, *feats]))
+
+    def forward(self, image_dict: dict[str, torch.Tensor], mask_dict: dict[str, torch.Tensor] | None = None,
+                reduce: str = "all") -> torch.Tensor:
+        """-> logits (B, out_chans) (cinema/convvit.py:512-561).  ``reduce``: "patch" (mean of per-view heads over the
+        patch means), "all" (the same plus the cls head) or "cls"."""
+        x = self.feature_forward(image_dict=image_dict, mask_dict=mask_dict)
+        if reduce == "cls":
+            return self.pred_head_dict["cls"](x["cls"])[:, 0]
+        if reduce not in ("patch", "all"):
+            raise NotImplementedError(f"Unsupported reduce method {reduce}.")
+        logits = [self.pred_head_dict[v](x[v].mean(dim=1, keepdim=True)) for v in self.views]
+        if reduce == "all":
+            logits.append(self.pred_head_dict["cls"](x["cls"]))
+        return torch.concat(logits, dim=1).mean(dim=1)
+
+    @classmethod
+    def from_finetuned(cls, config=None, state_dict=None, **kwargs) -> "ConvViT":
+        """Fine-tuned model from a reference-format config and state dict.  The reference fetches both from the Hugging
+        Face hub (cinema/convvit.py:563-591); offline they are passed in or read from ``config_path`` / ``weights_path``."""
+        if config is None:
+            import yaml
+
+            with open(kwargs["config_path"]) as f:
+                config = yaml.safe_load(f)
+        model = get_model(config)
+        if state_dict is None and "weights_path" in kwargs:
+            from safetensors.torch import load_file
+
+            state_dict = load_file(kwargs["weights_path"])
+        if state_dict is not None:
+            model.load_state_dict(state_dict)
+        return model
+
+    @classmethod
+    def from_pretrained(cls, config, freeze: bool, ckpt_path=None, **kwargs) -> "ConvViT":  # noqa: ARG003
+        """Model from config with the encoder initialised from an MAE checkpoint (cinema/convvit.py:593-613); the
+        checkpoint is a local ``.pt`` / ``.safetensors`` file (no hub access here)."""
+        from pathlib import Path
+
+        model = get_model(config)
+        if ckpt_path is None:
+            raise ValueError("ckpt_path (local MAE checkpoint) is required: there is no network to download one")
+        views = config["model"]["views"] if isinstance(config, dict) else config.model.views
+        return load_pretrain_weights(model=model, views=views, ckpt_path=Path(ckpt_path), freeze=freeze)
+
+
+def get_model(config) -> ConvViT:
+    """Config -> ConvViT as cinema/convvit.py:294-331 (``config`` is a nested dict or an OmegaConf object)."""
+    from cinema_b200.mae import _Cfg
+    from cinema_b200.vit import get_vit_config
+
+    c = _Cfg(config)
+    views = [c.model.views] if isinstance(c.model.views, str) else list(c.model.views)
+    vit_config = get_vit_config(c.model.convvit.size)
+    data = config["data"] if isinstance(config, dict) else config.data
+    get = (lambda k: data.get(k)) if hasattr(data, "get") else (lambda k: getattr(data, k, None))
+    if get("class_column") is not None:
+        out_chans = len(get(get("class_column")))
+    elif get("regression_column") is not None:
+        out_chans = 1
+    else:
+        out_chans = c.model.out_chans
+    ndim = {v: 3 if v == "sax" else 2 for v in views}
+    model = ConvViT(
+        image_size_dict={v: tuple(c.data.sax.patch_size if v == "sax" else c.data.lax.patch_size) for v in views},
+        n_frames=c.model.n_frames,
+        in_chans_dict={v: c.data.sax.in_chans if v == "sax" else c.data.lax.in_chans for v in views},
+        out_chans=out_chans,
+        enc_patch_size_dict={v: tuple(c.model.convvit.enc_patch_size[:n]) for v, n in ndim.items()},
+        enc_scale_factor_dict={v: tuple(c.model.convvit.enc_scale_factor[:n]) for v, n in ndim.items()},
+        enc_conv_chans=list(c.model.convvit.enc_conv_chans), enc_conv_n_blocks=c.model.convvit.enc_conv_n_blocks,
+        enc_embed_dim=vit_config["enc_embed_dim"], enc_depth=vit_config["enc_depth"], enc_n_heads=vit_config["enc_n_heads"],
+        drop_path=c.model.convvit.drop_path,
+    )
+    model.set_grad_ckpt(c.grad_ckpt)
+    return model
+
+
+_DROPPED_FROM_MAE = ("mask", "decoder", "_head", "sax", "lax_2c", "lax_3c", "lax_4c", "fusion", "dec_linear", "pos_embed")
+
+
+def load_pretrain_weights(model: nn.Module, views, ckpt_path, freeze: bool) -> nn.Module:
+    """Initialise a fine-tuning model from an MAE checkpoint (cinema/convvit.py:616-704): keep the shared encoder and the
+    stems (and fusions, if the model has them) of the requested views, drop decoder-side and positional tensors, tile
+    the first stem conv over extra input channels (n_frames > 1 / multi-modal input), verify that exactly the per-view
+    positional tables are missing, optionally freeze what was loaded."""
+    from pathlib import Path
+
+    ckpt_path = Path(ckpt_path)
+    if ckpt_path.suffix == ".pt":
+        pretrained = torch.load(ckpt_path, map_location="cpu")["model"]
+    elif ckpt_path.suffix == ".safetensors":
+        from safetensors.torch import load_file
+
+        pretrained = load_file(str(ckpt_path), device="cpu")
+    else:
+        raise ValueError(f"Unsupported checkpoint format {ckpt_path.suffix}.")
+    views = [views] if isinstance(views, str) else list(views)
+    drop = [k for k in _DROPPED_FROM_MAE if k not in views and not (k == "fusion" and hasattr(model, "enc_fusion_dict"))]
+    expected_missing = {f"enc_down_dict.{v}.pos_embed" for v in views}
+    first_conv = {f"enc_down_dict.{v}.conv_blocks.0.patch_embed.conv.weight": v for v in views}
+    state_dict = {}
+    for key, val in pretrained.items():
+        if any(tag in key for tag in drop):
+            continue
+        if key in first_conv:
+            chans = model.enc_down_dict[first_conv[key]].conv_blocks[0].patch_embed.conv.weight.shape[1]
+            if val.shape[1] != chans:
+                if val.ndim not in (4, 5):
+                    raise ValueError(f"Unsupported weight shape {val.shape}.")
+                val = val.repeat(1, chans, *([1] * (val.ndim - 2)))
+        state_dict[key] = val
+    result = model.load_state_dict(state_dict, strict=False)
+    missing = {k for k in result.missing_keys if "decoder" not in k and not k.startswith("dec_") and "head" not in k}
+    if missing != expected_missing:
+        raise ValueError(f"Missing keys from checkpoint: {sorted(missing)}, expected {sorted(expected_missing)}")
+    if result.unexpected_keys:
+        raise ValueError(f"Unexpected keys in checkpoint: {result.unexpected_keys}")
+    if freeze:
+        for name, p in model.named_parameters():
+            if name in state_dict:
+                p.requires_grad = False
+    return model
+
+
+def get_layer_id_for_vit(name: str, n_layers: int) -> int:
+    """Layer index of a parameter for layer-wise lr decay (cinema/convvit.py:707-736): stem / embeddings 0, encoder
+    block i -> i + 1, everything else (heads) ``n_layers``."""
+    if name.startswith("enc_") or any(tag in name for tag in ("cls_token", "pos_embed", "patch_embed", "view_embed")):
+        return 0
+    if name.startswith("encoder.blocks"):
+        return int(name.split(".")[2]) + 1
+    return n_layers
+
+
+def param_groups_lr_decay(model: nn.Module, no_weight_decay_list: list[str], weight_decay: float, layer_decay: float,
+                          out_dir=None) -> list[dict]:
+    """AdamW parameter groups with layer-wise lr decay (cinema/convvit.py:739-816): group = (layer id, decay or not),
+    ``lr_scale = layer_decay ** (n_layers - layer_id)``; 1-D parameters and the listed names are not decayed.  With
+    ``out_dir`` the group -> parameter-name table is written to ``param_group_names.json`` like the reference does."""
+    n_layers = len(model.encoder.blocks) + 1
+    names: dict[str, dict] = {}
+    groups: dict[str, dict] = {}
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        no_decay = p.ndim == 1 or n in no_weight_decay_list
+        layer_id = get_layer_id_for_vit(n, n_layers)
+        key = f"layer_{layer_id}_{'no_decay' if no_decay else 'decay'}"
+        if key not in groups:
+            meta = {"lr_scale": layer_decay ** (n_layers - layer_id), "weight_decay": 0.0 if no_decay else weight_decay}
+            names[key] = {**meta, "params": []}
+            groups[key] = {**meta, "params": []}
+        names[key]["params"].append(n)
+        groups[key]["params"].append(p)
+    if out_dir is not None:
+        import json
+        from pathlib import Path
+
+        Path(out_dir).mkdir(parents=True, exist_ok=True)
+        with open(Path(out_dir) / "param_group_names.json", "w", encoding="utf-8") as f:
+            json.dump(names, f, indent=2)
+    return list(groups.values())

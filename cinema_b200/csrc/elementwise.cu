@@ -148,20 +148,22 @@ __global__ void colsum_seg_f32_kernel(const float* __restrict__ X, long long bst
   atomicAdd(out + col, acc);
 }
 
-// dst = bf16(src * scale_host * (scale_dev ? *scale_dev : 1))
+// dst = bf16(src * scale_host * (scale_dev ? scale_dev[g] : 1)), g = element / group (group == 0: one scalar, g = 0;
+// otherwise group is a multiple of 4 elements: per-sample factors of stochastic depth)
 __global__ void scale_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n,
-                                  const float* __restrict__ scale_dev, float scale) {
+                                  const float* __restrict__ scale_dev, float scale, long long group) {
   pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
-  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  const float sc0 = scale * ((scale_dev && group == 0) ? __ldg(scale_dev) : 1.0f);
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const float sc = group > 0 ? sc0 * __ldg(scale_dev + (i << 2) / group) : sc0;
     reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(a.x * sc, a.y * sc), pack_bf16(a.z * sc, a.w * sc));
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    dst[i] = __float2bfloat16_rn(src[i] * sc);
+    dst[i] = __float2bfloat16_rn(src[i] * sc0);  // (a ragged tail only exists in scalar mode: group % 4 == 0 divides n)
   }
 }
 
@@ -494,10 +496,12 @@ extern "C" int cb_colsum_seg_f32(const float* X, long long bstride_rows, long lo
 }
 
 extern "C" int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale,
-                                  void* stream) {
+                                  long long group, void* stream) {
   if (n <= 0) return 0;
+  CB_CHECK_ARG(group == 0 || (scale_dev != nullptr && group % 4 == 0 && n % group == 0),
+               "scale_cast: grouped mode needs device factors and a group size that is a multiple of 4 dividing n");
   CB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "scale_cast: buffers must be 16/8-byte aligned");
-  cb_launch(scale_cast_kernel, blocks_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n, scale_dev, scale);
+  cb_launch(scale_cast_kernel, blocks_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n, scale_dev, scale, group);
   CB_LAUNCH_CHECK();
   return 0;
 }

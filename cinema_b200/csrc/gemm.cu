@@ -44,6 +44,8 @@ struct GemmArgs {
   int epi;
   float alpha;
   float* colsum;  // optional: column sums of the bf16 output (bias gradient of the consumer)
+  const float* row_scale;  // optional: per row-group factor on (alpha * acc + bias) before the residual (stochastic depth)
+  int rows_per_group;
 };
 
 // CTAS == 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2; each
@@ -219,6 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool has_aux = p.epi == CB_EPI_GELU_BWD;
     const bool has_bias = p.bias != nullptr;
     const bool has_out2 = p.out2 != nullptr;
+    const bool has_rs = p.row_scale != nullptr;
     // all epilogue addressing is base pointer + 32-bit element offset (host checks M * ld < 2^31): one IMAD.WIDE per
     // access instead of 64-bit row arithmetic, which used to be half of the epilogue's instructions
     const int so8 = (int)(8 * p.ldo), s28 = (int)(8 * p.ldo2), sr8 = (int)(8 * p.ldr), sa8 = (int)(8 * p.ldaux);
@@ -242,6 +245,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t vmask = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) vmask |= (r0 + 8 * i < p.M ? 1u : 0u) << i;
+      float rs[4] = {1.f, 1.f, 1.f, 1.f};
+      if ((MODE == 0 || MODE == 3) && has_rs) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((vmask >> i) & 1u) rs[i] = __ldg(p.row_scale + (r0 + 8 * i) / p.rows_per_group);
+      }
       const int oo = (int)((long long)r0 * p.ldo) + colw;
       const int o2 = (int)((long long)r0 * p.ldo2) + colw;
       const int ro = (int)((long long)r0 * p.ldr) + colw;
@@ -340,6 +349,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           } else if constexpr (MODE == 4) {
             red_add_v4(out32 + eo, v[0], v[1], v[2], v[3]);
           } else {
+            if (has_rs) v[0] *= rs[i], v[1] *= rs[i], v[2] *= rs[i], v[3] *= rs[i];
             if (has_res) v[0] += res[i].x, v[1] += res[i].y, v[2] += res[i].z, v[3] += res[i].w;
             const uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
             if constexpr (MODE == 3) {
@@ -455,7 +465,8 @@ int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void*
 extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                             int M, int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2,
                             long long ldo2, const float* bias, const float* residual, long long ldr, const void* aux,
-                            long long ldaux, int epilogue, float alpha, int split_k, int block_n, float* colsum, void* stream) {
+                            long long ldaux, int epilogue, float alpha, int split_k, int block_n, float* colsum,
+                            const float* row_scale, int rows_per_group, void* stream) {
   CB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CB_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   CB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B TMA pitch)");
@@ -484,6 +495,9 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
   p.bias = bias, p.residual = residual, p.ldr = ldr;
   p.aux = reinterpret_cast<const bf16*>(aux), p.ldaux = ldaux;
   p.epi = epilogue, p.alpha = alpha, p.colsum = colsum;
+  p.row_scale = row_scale, p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  CB_CHECK_ARG(row_scale == nullptr || (epilogue == CB_EPI_NONE && !accumulate && rows_per_group > 0),
+               "gemm: row_scale needs the plain epilogue, a non-accumulating output and rows_per_group > 0");
   CB_CHECK_ARG(colsum == nullptr || (out_dtype == CB_DT_BF16 && epilogue != CB_EPI_GELU && !accumulate),
                "gemm: colsum needs a bf16 output without the GELU epilogue");
   CB_CHECK_ARG(((uintptr_t)colsum & 15) == 0, "gemm: colsum must be 16-byte aligned");

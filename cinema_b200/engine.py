@@ -78,12 +78,13 @@ def linw_fused(arena: ParamArena, weights: list[nn.Parameter], biases: list[nn.P
 # linear
 # ------------------------------------------------------------------------------------------
 def linear_fwd(x16: torch.Tensor, w: LinW, *, out_dtype: torch.dtype = BF16, residual: torch.Tensor | None = None,
-               out: torch.Tensor | None = None) -> torch.Tensor:
-    """y = x W^T + b (+ residual).  x16 (M, K) bf16 -> (M, N) bf16 / fp32."""
+               out: torch.Tensor | None = None, row_scale: torch.Tensor | None = None, rows_per_group: int = 0) -> torch.Tensor:
+    """y = s * (x W^T + b) (+ residual).  x16 (M, K) bf16 -> (M, N) bf16 / fp32; ``row_scale`` s: one fp32 factor per
+    ``rows_per_group`` rows (stochastic depth), default 1."""
     m = x16.shape[0]
     if out is None:
         out = torch.empty((m, w.n), dtype=out_dtype, device=x16.device)
-    _C.gemm(x16, w.w16, out, bias=w.bias, residual=residual)
+    _C.gemm(x16, w.w16, out, bias=w.bias, residual=residual, row_scale=row_scale, rows_per_group=rows_per_group)
     return out
 
 
@@ -215,22 +216,46 @@ class BlockW:
     fc2: LinW
     n_heads: int
     scale: float
+    drop_prob: float = 0.0  # stochastic depth of both residual branches (active in training mode only)
+    drop_scale_by_keep: bool = True
+
+
+def draw_drop_scales(b: int, drop_prob: float, scale_by_keep: bool, device: torch.device) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-sample factors of the two DropPath layers of a block, drawn in the reference's order (attention branch, then
+    MLP branch): Bernoulli(keep) / keep, timm ``drop_path`` semantics (cinema/vit.py:562,577)."""
+    keep = 1.0 - drop_prob
+    out = []
+    for _ in range(2):
+        t = torch.empty(b, dtype=F32, device=device).bernoulli_(keep)
+        if keep > 0.0 and scale_by_keep:
+            t.div_(keep)
+        out.append(t)
+    return out[0], out[1]
+
+
+def out_bias_of(ws: "list[BlockW]", j: int, d: int) -> torch.Tensor | None:
+    """``fc2.bias`` gradient buffer of block ``j`` if the kernel producing that block's output gradient may accumulate it
+    (:func:`fusable_bias`); not with stochastic depth, where the branch sees a per-sample scaled gradient."""
+    if j < 0 or ws[j].drop_prob > 0.0:
+        return None
+    return fusable_bias(ws[j].fc2, d)
 
 
 def blockw(arena: ParamArena, blk: nn.Module, train: bool) -> BlockW:
     at = blk.attn
     if not isinstance(blk.norm1, nn.LayerNorm) or not isinstance(blk.norm2, nn.LayerNorm):
         raise NotImplementedError("the B200 block path supports nn.LayerNorm only")
-    if not isinstance(at.q_norm, nn.Identity) or not isinstance(blk.ls1, nn.Identity) or blk.training and (
-            not isinstance(blk.drop_path1, nn.Identity)):
-        raise NotImplementedError("qk_norm / LayerScale / DropPath are not part of the MAE hot path (cinema/vit.py:561-577)")
+    if not isinstance(at.q_norm, nn.Identity) or not isinstance(blk.ls1, nn.Identity):
+        raise NotImplementedError("qk_norm / LayerScale are not part of the MAE hot path (cinema/vit.py:561-577)")
+    dp = blk.drop_path1
+    drop_prob = float(getattr(dp, "drop_prob", 0.0)) if blk.training and not isinstance(dp, nn.Identity) else 0.0
     return BlockW(
         normw(arena, blk.norm1, train), normw(arena, blk.norm2, train),
         linw_fused(arena, [at.q.weight, at.kv.weight], [at.q.bias, at.kv.bias], train),
         linw(arena, at.q.weight, at.q.bias, train), linw(arena, at.kv.weight, at.kv.bias, train),
         linw(arena, at.proj.weight, at.proj.bias, train),
         linw(arena, blk.mlp.fc1.weight, blk.mlp.fc1.bias, train), linw(arena, blk.mlp.fc2.weight, blk.mlp.fc2.bias, train),
-        at.n_heads, float(at.scale),
+        at.n_heads, float(at.scale), drop_prob, bool(getattr(dp, "scale_by_keep", True)),
     )
 
 
@@ -252,6 +277,8 @@ def block_fwd(x: torch.Tensor, w: BlockW, b: int, kv: tuple[torch.Tensor, torch.
     m, d = x.shape
     n = m // b
     hd = d // w.n_heads
+    drop = draw_drop_scales(b, w.drop_prob, w.drop_scale_by_keep, x.device) if w.drop_prob > 0.0 else None
+    s1, s2 = drop if drop is not None else (None, None)
     h1, _, mean1, rstd1 = ln_fwd(x, w.norm1, stats=save)
     if kv is None:
         qkv = _self_qkv_fwd(h1, w)
@@ -265,13 +292,13 @@ def block_fwd(x: torch.Tensor, w: BlockW, b: int, kv: tuple[torch.Tensor, torch.
         qsave = q2
     o, lse = attn_fwd(q, k, v, w.scale)
     o2 = o.view(m, d)
-    x1 = linear_fwd(o2, w.proj, out_dtype=F32, residual=x)
+    x1 = linear_fwd(o2, w.proj, out_dtype=F32, residual=x, row_scale=s1, rows_per_group=n)
     h2, _, mean2, rstd2 = ln_fwd(x1, w.norm2, stats=save)
     pre, act = linear_gelu_fwd(h2, w.fc1)
-    x2 = linear_fwd(act, w.fc2, out_dtype=F32, residual=x1)
+    x2 = linear_fwd(act, w.fc2, out_dtype=F32, residual=x1, row_scale=s2, rows_per_group=n)
     if not save:
         return x2, None
-    return x2, (x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act)
+    return x2, (x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act, drop)
 
 
 def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
@@ -281,16 +308,26 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
     For cross-attention ``dkv`` are the (dk, dv) views this block's key / value gradients are written to.
     ``fc2_bias_done``: the producer of ``dx16`` already accumulated ``fc2.bias``'s gradient; ``out_bias``: bias-gradient
     buffer of the Linear that consumes the returned dx16 as its output gradient (fused into the last LayerNorm backward).
+    With stochastic depth (``saved[-1]`` = the per-sample factors of the forward) each branch sees s_b * dx: the bf16
+    branch gradient is re-derived from dx32 by one scale-and-cast pass and the bias-gradient fusions across the residual
+    are off (callers use :func:`out_bias_of`).
     Returns the (fp32, bf16) gradient of the block input; dx32 is updated in place."""
-    x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act = saved
+    x, mean1, rstd1, h1, qsave, o2, lse, x1, mean2, rstd2, h2, pre, act, drop = saved
     m, d = x.shape
     n = m // b
     hd = d // w.n_heads
+    if drop is not None:
+        if fc2_bias_done:
+            raise ValueError("fc2 bias gradient cannot be pre-accumulated for a block with stochastic depth")
+        dx16 = torch.empty((m, d), dtype=BF16, device=x.device)
+        _C.scale_cast(dx32, dx16, drop[1], group=n * d)
     # ---- MLP path
     dpre = linear_bwd(dx16, act, w.fc2, gelu_aux=pre, bias_done=fc2_bias_done, dx_colsum=w.fc1.gb)
     dh2 = linear_bwd(dpre, h2, w.fc1, bias_done=w.fc1.gb is not None)
-    proj_gb = fusable_bias(w.proj, d)
+    proj_gb = fusable_bias(w.proj, d) if drop is None else None
     dx32, dx16 = ln_bwd(dh2, x1, mean2, rstd2, w.norm2, dres=dx32, dx32=dx32, dxsum=proj_gb)
+    if drop is not None:
+        _C.scale_cast(dx32, dx16, drop[0], group=n * d)
     # ---- attention path
     do2 = linear_bwd(dx16, o2, w.proj, bias_done=proj_gb is not None)
     do = do2.view(b, n, w.n_heads, hd)

@@ -249,7 +249,7 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
                     _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
     vs.join()
     ew = st.enc_w
-    gb_of = lambda j: engine.fusable_bias(ew[j].fc2, d) if j >= 0 else None  # noqa: E731
+    gb_of = lambda j: engine.out_bias_of(ew, j, d)  # noqa: E731
     dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm,
                                dxsum=gb_of(len(ew) - 1))
     for j in range(len(ew) - 1, -1, -1):
@@ -516,7 +516,7 @@ class _MAEFn(torch.autograd.Function):
                 _C.scatter_rows(ddv.view(b, nm, dd), q_rows[i], ddec)
         vs.join()
         dec_w = s["dec_w"]
-        dgb_of = lambda j: engine.fusable_bias(dec_w[j].fc2, dd) if j >= 0 else None  # noqa: E731
+        dgb_of = lambda j: engine.out_bias_of(dec_w, j, dd)  # noqa: E731
         dx32, dx16 = engine.ln_bwd(ddec.view(b * nq, dd), s["dec_last"], s["dmean"], s["drstd"], s["dec_norm"],
                                    dxsum=dgb_of(len(dec_w) - 1))
         cross = s["cross"]

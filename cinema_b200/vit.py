@@ -452,7 +452,10 @@ class Block(nn.Module):
 
 
 class DropPath(nn.Module):
-    """Stochastic depth placeholder: only used when fine-tuning (drop_path > 0); identity in eval / pretraining."""
+    """Stochastic depth per sample (timm ``DropPath``, used at cinema/vit.py:562,577 when fine-tuning with drop_path > 0).
+    Inside a ``Block`` it never runs as a module: the per-sample keep / keep_prob factors are drawn by
+    ``engine.draw_drop_scales`` and applied in the epilogue of the branch's last GEMM.  Called on its own it is the plain
+    elementwise definition."""
 
     def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True) -> None:
         super().__init__()
@@ -462,7 +465,14 @@ class DropPath(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.drop_prob == 0.0 or not self.training:
             return x
-        raise NotImplementedError("DropPath > 0 in training mode is outside the MAE pre-training hot path")
+        keep = 1.0 - self.drop_prob
+        t = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            t.div_(keep)
+        return x * t
+
+    def extra_repr(self) -> str:
+        return f"drop_prob={round(self.drop_prob, 3):0.3f}"
 
 
 class ViTEncoder(nn.Module):

@@ -43,6 +43,9 @@ int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * split_k: 0 = auto (only ever >1 when accumulate=1).  block_n: 0 = auto, or 64/128/256.
  * colsum (fp32 [N], may be NULL; bf16-output epilogues without GELU only): colsum[n] += sum_m of the bf16 values stored to
  * out -- the bias gradient of the Linear layer that consumes `out` as its output gradient (no separate column-sum pass).
+ * row_scale (fp32 [ceil(M / rows_per_group)], may be NULL; plain epilogue, non-accumulating): the value alpha*acc+bias of
+ * row m is multiplied by row_scale[m / rows_per_group] before the residual is added -- timm DropPath (stochastic depth,
+ * per-sample keep / keep_prob factors) of cinema/vit.py:562,577,606,608 fused into the branch's last Linear.
  * Replaces nn.Linear forward/backward: cinema/vit.py:472-477,498-499,520 (q, kv, proj),
  * timm Mlp fc1/GELU/fc2 (cinema/vit.py:570-575), cinema/vit.py:294-298,342 (PatchEmbed.proj),
  * cinema/convvit.py:121,205 (linear), cinema/convvit.py:252,284 (k==s down convs as GEMM),
@@ -50,7 +53,8 @@ int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
                  int N, int K, void* out, long long ldo, int out_dtype, int accumulate, void* out2, long long ldo2,
                  const float* bias, const float* residual, long long ldr, const void* aux, long long ldaux,
-                 int epilogue, float alpha, int split_k, int block_n, float* colsum, void* stream);
+                 int epilogue, float alpha, int split_k, int block_n, float* colsum, const float* row_scale,
+                 int rows_per_group, void* stream);
 
 /* column sums of a bf16 [M,N] matrix accumulated (atomically) into fp32 out[N]: bias gradients.
  * Replaces the reduce kernels autograd runs for nn.Linear bias (same call sites as above). */
@@ -126,8 +130,10 @@ int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, cons
  * the backward of the broadcast in cinema/vit.py:672 and cinema/mae/mae.py:98-99. */
 int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int B, int k, int D, float* out,
                       void* stream);
-/* dst[i] = bf16(src[i] * scale * (scale_dev ? *scale_dev : 1)) */
-int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale, void* stream);
+/* dst[i] = bf16(src[i] * scale * f), f = 1 (scale_dev NULL), *scale_dev (group == 0) or scale_dev[i / group] (group > 0,
+ * a multiple of 4 dividing n: per-sample factors, the backward of DropPath, cinema/vit.py:606,608) */
+int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale, long long group,
+                       void* stream);
 
 /* patchify / unpatchify of a contiguous (B, C, S1..Sn) tensor, n in 1..4, element size 2 or 4 bytes:
  * tokens (B, prod(grid), prod(patch)*C), channel fastest ("nchpwqdr->nhwdpqrc", cinema/vit.py:67-256).

@@ -273,21 +273,27 @@ def mlp(sd: StateDict, name: str, x: Tensor) -> Tensor:
     return _lin(sd, f"{name}.fc2", F.gelu(_lin(sd, f"{name}.fc1", x)))
 
 
-def block(sd: StateDict, name: str, q: Tensor, k: Tensor | None, n_heads: int, eps: float, rotary: bool = False):
-    """Block.forward (cinema/vit.py:587-609).  Only q is layer-normed; k is used as given."""
-    q = q + attention(sd, f"{name}.attn", _ln(sd, f"{name}.norm1", q, eps), k, n_heads, rotary)
-    q = q + mlp(sd, f"{name}.mlp", _ln(sd, f"{name}.norm2", q, eps))
+def block(sd: StateDict, name: str, q: Tensor, k: Tensor | None, n_heads: int, eps: float, rotary: bool = False,
+          drop: tuple[Tensor, Tensor] | None = None):
+    """Block.forward (cinema/vit.py:587-609).  Only q is layer-normed; k is used as given.  ``drop``: the per-sample
+    factors (B,) of drop_path1 / drop_path2 in training mode (timm DropPath: Bernoulli(keep) / keep), None = identity."""
+    h = attention(sd, f"{name}.attn", _ln(sd, f"{name}.norm1", q, eps), k, n_heads, rotary)
+    q = q + (h if drop is None else h * drop[0].to(h.dtype).view(-1, 1, 1))
+    h = mlp(sd, f"{name}.mlp", _ln(sd, f"{name}.norm2", q, eps))
+    q = q + (h if drop is None else h * drop[1].to(h.dtype).view(-1, 1, 1))
     return q
 
 
 def vit_encoder(sd: StateDict, name: str, x: Tensor, depth: int, n_heads: int, eps: float, rotary: bool = False,
-                return_all: bool = False):
-    """ViTEncoder.forward / feature_forward (cinema/vit.py:661-698)."""
+                return_all: bool = False, drop_scales: list[Tensor] | None = None):
+    """ViTEncoder.forward / feature_forward (cinema/vit.py:661-698).  ``drop_scales``: 2 * depth stochastic-depth
+    factor vectors in call order (see :func:`block`)."""
     cls = sd[f"{name}.cls_token"].expand(x.shape[0], -1, -1)
     x = torch.cat([cls, x], dim=1)
     feats = []
     for i in range(depth):
-        x = block(sd, f"{name}.blocks.{i}", x, None, n_heads, eps, rotary)
+        x = block(sd, f"{name}.blocks.{i}", x, None, n_heads, eps, rotary,
+                  None if drop_scales is None else (drop_scales[2 * i], drop_scales[2 * i + 1]))
         if i != depth - 1:
             feats.append(x)
     x = _ln(sd, f"{name}.norm", x, eps)
@@ -351,11 +357,11 @@ def masked_conv_block(sd: StateDict, name: str, x: Tensor, vis: Tensor | None, e
 
 
 def downsample_encoder(sd: StateDict, name: str, cfg: MAEConfig, view: str, image: Tensor, mask: Tensor | None):
-    """DownsampleEncoder.forward (cinema/convvit.py:165-207).  Returns (skips, tokens(B, n_patches, D))
-    for an input whose size equals the configured image size (no pos-embed interpolation)."""
+    """DownsampleEncoder.forward (cinema/convvit.py:165-207).  Returns (skips, tokens(B, n_patches, D)); an input
+    whose size differs from the configured image size gets the resampled positional table (cinema/convvit.py:139-163)."""
     b = image.shape[0]
     sizes = cfg.patch_sizes(view)
-    grid = cfg.grid_size(view)
+    grid = tuple(s // p for s, p in zip(image.shape[2:], cfg.dec_patch_size(view)))
     n_levels = len(cfg.enc_conv_chans)
     vis_masks: list[Tensor | None] = [None] * n_levels
     if mask is not None:
@@ -371,8 +377,19 @@ def downsample_encoder(sd: StateDict, name: str, cfg: MAEConfig, view: str, imag
             x = masked_conv_block(sd, f"{name}.conv_blocks.{lvl}.conv.{j}", x, vis_masks[lvl], cfg.conv_norm_eps)
         skips.append(x)
     tok = _lin(sd, f"{name}.patch_embed.proj", patchify(x, sizes[-1]))
-    tok = _lin(sd, f"{name}.linear", tok) + sd[f"{name}.pos_embed"]
+    tok = _lin(sd, f"{name}.linear", tok) + interpolate_pos_embed(sd[f"{name}.pos_embed"], cfg.grid_size(view), grid)
     return skips, tok
+
+
+def interpolate_pos_embed(pos: Tensor, grid_from: tuple[int, ...], grid_to: tuple[int, ...]) -> Tensor:
+    """DownsampleEncoder.interpolate_pos_encoding (cinema/convvit.py:139-163): bicubic (2-D) / trilinear (3-D)
+    resampling of the (1, n, D) table, identity when the grids agree."""
+    if tuple(grid_from) == tuple(grid_to):
+        return pos
+    d = pos.shape[-1]
+    t = pos.float().reshape(1, *grid_from, d).movedim(-1, 1)
+    t = F.interpolate(t, size=tuple(grid_to), mode={2: "bicubic", 3: "trilinear"}[len(grid_to)], antialias=False)
+    return t.movedim(1, -1).reshape(1, -1, d).to(pos.dtype)
 
 
 def _gather_rows(x: Tensor, sel: Tensor) -> Tensor:
@@ -504,6 +521,53 @@ def mae_feature_forward(sd: StateDict, cfg: MAEConfig, image_dict: dict[str, Ten
     for i, v in enumerate(views):
         parts[i + 1] = multi_scale_fusion(sd, f"enc_fusion_dict.{v}", cfg, v, skips_all[i], parts[i + 1], None)
     return dict(zip(["cls", *views], parts))
+
+
+# --------------------------------------------------------------------------------------
+# ConvViT: classification / regression fine-tuning model (cinema/convvit.py:334-561)
+# --------------------------------------------------------------------------------------
+def convvit_config(kw: dict) -> MAEConfig:
+    """ConvViT constructor arguments -> the config object the stem / encoder restatements read (decoder fields unused).
+    The stem sees ``n_frames * in_chans`` channels (cinema/convvit.py:400)."""
+    return MAEConfig(
+        image_size_dict=kw["image_size_dict"], in_chans_dict={v: kw["n_frames"] * c for v, c in kw["in_chans_dict"].items()},
+        enc_patch_size_dict=kw["enc_patch_size_dict"], enc_scale_factor_dict=kw["enc_scale_factor_dict"],
+        enc_conv_chans=kw["enc_conv_chans"], enc_conv_n_blocks=kw["enc_conv_n_blocks"], enc_embed_dim=kw["enc_embed_dim"],
+        enc_depth=kw["enc_depth"], enc_n_heads=kw["enc_n_heads"], dec_embed_dim=0, dec_depth=0, dec_n_heads=1,
+        mlp_ratio=kw.get("mlp_ratio", 4), norm_eps=kw.get("norm_eps", 1e-5), rotary=kw.get("rotary", False),
+    )
+
+
+def convvit_feature_forward(sd: StateDict, cfg: MAEConfig, image_dict: dict[str, Tensor],
+                            mask_dict: dict[str, Tensor] | None, drop_scales: list[Tensor] | None = None) -> dict[str, Tensor]:
+    """ConvViT.feature_forward (cinema/convvit.py:464-510): the mask only reaches the stem; every token is encoded and
+    the fusion runs unmasked."""
+    views = list(image_dict.keys())
+    xs, skips_all, ns = [], [], []
+    for v in views:
+        skips, tok = downsample_encoder(sd, f"enc_down_dict.{v}", cfg, v, image_dict[v],
+                                        None if mask_dict is None else mask_dict[v])
+        skips_all.append(skips), xs.append(tok), ns.append(tok.shape[1])
+    x = vit_encoder(sd, "encoder", torch.cat(xs, dim=1), cfg.enc_depth, cfg.enc_n_heads, cfg.norm_eps, cfg.rotary,
+                    drop_scales=drop_scales)
+    parts = list(torch.split(x, [1, *ns], dim=1))
+    for i, v in enumerate(views):
+        parts[i + 1] = multi_scale_fusion(sd, f"enc_fusion_dict.{v}", cfg, v, skips_all[i], parts[i + 1], None)
+    return dict(zip(["cls", *views], parts))
+
+
+def convvit_forward(sd: StateDict, cfg: MAEConfig, image_dict: dict[str, Tensor], mask_dict: dict[str, Tensor] | None,
+                    reduce: str = "all", drop_scales: list[Tensor] | None = None) -> Tensor:
+    """ConvViT.forward (cinema/convvit.py:512-561): per-view heads on the patch means (+ cls head), averaged."""
+    x = convvit_feature_forward(sd, cfg, image_dict, mask_dict, drop_scales)
+    if reduce == "cls":
+        return _lin(sd, "pred_head_dict.cls", x["cls"])[:, 0]
+    if reduce not in ("patch", "all"):
+        raise NotImplementedError(f"Unsupported reduce method {reduce}.")
+    logits = [_lin(sd, f"pred_head_dict.{v}", x[v].mean(dim=1, keepdim=True)) for v in cfg.views]
+    if reduce == "all":
+        logits.append(_lin(sd, "pred_head_dict.cls", x["cls"]))
+    return torch.concat(logits, dim=1).mean(dim=1)
 
 
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ def _gelu_grad(x):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, accumulate=False, out2=None, bias=None, residual=None, aux=None,
-         epilogue=EPI_NONE, alpha=1.0, split_k=0, block_n=0, colsum=None):
+         epilogue=EPI_NONE, alpha=1.0, split_k=0, block_n=0, colsum=None, row_scale=None, rows_per_group=0):
     assert a.dtype == BF16 and b.dtype == BF16
     am = a.float().t() if a_mn else a.float()
     bm = b.float() if b_mn else b.float().t()  # (K, N)
@@ -44,6 +44,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, accumulate=False, out2=None, bias
         return
     if epilogue == EPI_GELU_BWD:
         acc = acc * _gelu_grad(aux.float())
+    if row_scale is not None:
+        assert epilogue == EPI_NONE and not accumulate and rows_per_group > 0
+        acc = acc * row_scale.float().repeat_interleave(rows_per_group)[:acc.shape[0], None]
     if residual is not None:
         acc = acc + residual
     if accumulate:
@@ -174,7 +177,11 @@ def colsum_seg(x, off, k, out):
     out.add_(x[:, off:off + k].sum(dim=(0, 1)))
 
 
-def scale_cast(src, dst, scale_dev=None, scale=1.0):
+def scale_cast(src, dst, scale_dev=None, scale=1.0, group=0):
+    if group:
+        f = scale_dev.float().repeat_interleave(group).view(src.shape)
+        dst.copy_((src * (scale * f)).to(BF16))
+        return
     s = scale * (float(scale_dev.reshape(-1)[0]) if scale_dev is not None else 1.0)
     dst.copy_((src * s).to(BF16))
 

@@ -24,6 +24,7 @@ import torch
 from torch import nn
 
 REF = Path("/root/reference")
+DROP_LOG: list = []
 OUT = Path(__file__).resolve().parent
 
 
@@ -80,6 +81,7 @@ def install_shims() -> None:
             t = x.new_empty(shape).bernoulli_(keep)
             if keep > 0.0 and self.scale_by_keep:
                 t.div_(keep)
+            DROP_LOG.append(t.flatten().clone())  # per-sample factors in call order, replayed by the parity tests
             return x * t
 
     class LayerScale(nn.Module):
@@ -217,6 +219,144 @@ def make_mae_case(name: str, spec: dict) -> None:
     print(name, float(loss), {k: tuple(v.shape) for k, v in preds.items()})
 
 
+CONVVIT_CASES = {
+    # two views (3-D SAX + 2-D LAX), head_dim 32, two stem levels, 3 classes
+    "convvit_2view": dict(
+        kw=dict(
+            image_size_dict={"sax": (32, 32, 4), "lax_2c": (32, 32)}, in_chans_dict={"sax": 1, "lax_2c": 1}, n_frames=1,
+            out_chans=3, enc_patch_size_dict={"sax": (4, 4, 1), "lax_2c": (4, 4)},
+            enc_scale_factor_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)}, enc_conv_chans=[8, 16], enc_conv_n_blocks=1,
+            enc_embed_dim=64, enc_depth=2, enc_n_heads=2,
+        ),
+        batch=2, input_size=None,
+    ),
+    # video-style input (n_frames * in_chans channels), head_dim 64, input larger than the configured image size
+    # (interpolated positional table), regression head
+    "convvit_frames_resized": dict(
+        kw=dict(
+            image_size_dict={"sax": (32, 32, 2)}, in_chans_dict={"sax": 2}, n_frames=3, out_chans=1,
+            enc_patch_size_dict={"sax": (4, 4, 1)}, enc_scale_factor_dict={"sax": (2, 2, 1)}, enc_conv_chans=[8, 16],
+            enc_conv_n_blocks=2, enc_embed_dim=64, enc_depth=1, enc_n_heads=1, mlp_ratio=2,
+        ),
+        batch=3, input_size={"sax": (48, 32, 2)},
+    ),
+    # stochastic depth as in the fine-tuning configs (drop_path > 0, training mode): the drawn per-sample factors are
+    # recorded (``drop_scales``, call order = attention branch, MLP branch per block) and replayed by the tests
+    "convvit_droppath": dict(
+        kw=dict(
+            image_size_dict={"sax": (32, 32, 4), "lax_2c": (32, 32)}, in_chans_dict={"sax": 1, "lax_2c": 1}, n_frames=1,
+            out_chans=2, enc_patch_size_dict={"sax": (4, 4, 1), "lax_2c": (4, 4)},
+            enc_scale_factor_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)}, enc_conv_chans=[8, 16], enc_conv_n_blocks=1,
+            enc_embed_dim=64, enc_depth=3, enc_n_heads=2, drop_path=0.4,
+        ),
+        batch=4, input_size=None,
+    ),
+}
+
+CONVVIT_GRAD_KEYS = [
+    "encoder.blocks.0.attn.q.weight", "encoder.blocks.0.mlp.fc2.bias", "encoder.cls_token", "encoder.norm.weight",
+    "enc_fusion_dict.sax.down_convs.0.weight", "enc_fusion_dict.sax.norm.bias", "enc_down_dict.sax.linear.weight",
+    "enc_down_dict.sax.conv_blocks.0.patch_embed.conv.weight", "enc_down_dict.sax.conv_blocks.1.conv.0.dw_conv.weight",
+    "pred_head_dict.sax.weight", "pred_head_dict.cls.bias",
+]
+
+
+def make_convvit_case(name: str, spec: dict) -> None:
+    """ConvViT (classification / regression fine-tuning model, cinema/convvit.py:334) forward for every ``reduce``,
+    with and without a stem mask, plus gradients of a weighted logit sum."""
+    install_shims()
+    from cinema.convvit import ConvViT, param_groups_lr_decay  # type: ignore
+
+    kw = spec["kw"]
+    torch.manual_seed(10)
+    model = ConvViT(**kw)
+    model.train()  # drop_path = 0: train and eval agree
+    g = torch.Generator().manual_seed(11)
+    sizes = spec["input_size"] or kw["image_size_dict"]
+    images = {v: torch.rand(spec["batch"], kw["n_frames"] * kw["in_chans_dict"][v], *sizes[v], generator=g) for v in sizes}
+    mask_dict = {}
+    for v in sizes:
+        grid = tuple(s // p for s, p in zip(sizes[v], model.enc_down_dict[v].eff_patch_size))
+        n = 1
+        for x in grid:
+            n *= x
+        mask_dict[v] = torch.rand(spec["batch"], n, generator=g) > 0.5
+    named = dict(model.named_parameters())
+    w = torch.rand(spec["batch"], kw["out_chans"], generator=g)
+    drop_scales = None
+    if kw.get("drop_path", 0.0) > 0.0:
+        torch.manual_seed(13)
+        del DROP_LOG[:]
+        out = model(images, None, "all")
+        drop_scales = [t.clone() for t in DROP_LOG]
+        assert len(drop_scales) == 2 * kw["enc_depth"] and any(bool((t == 0).any()) for t in drop_scales)
+        (out * w).sum().backward()
+        logits, logits_masked, grads_masked = {"all": out.detach()}, {}, {}
+        grads = {k: named[k].grad.clone() for k in CONVVIT_GRAD_KEYS if k in named and named[k].grad is not None}
+        model.eval()
+        feats = {k: v.detach() for k, v in model.feature_forward(images, None).items()}  # eval: DropPath is the identity
+        model.train()
+    else:
+        logits = {r: model(images, None, r).detach() for r in ("patch", "all", "cls")}
+        logits_masked = {r: model(images, mask_dict, r).detach() for r in ("all",)}
+        feats = {k: v.detach() for k, v in model.feature_forward(images, None).items()}
+        out = model(images, None, "all")
+        (out * w).sum().backward()
+        grads = {k: named[k].grad.clone() for k in CONVVIT_GRAD_KEYS if k in named and named[k].grad is not None}
+        model.zero_grad()
+        out = model(images, mask_dict, "all")
+        (out * w).sum().backward()
+        grads_masked = {k: named[k].grad.clone() for k in CONVVIT_GRAD_KEYS if k in named and named[k].grad is not None}
+    import json
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        groups = param_groups_lr_decay(model, ["encoder.cls_token"], weight_decay=0.05, layer_decay=0.75, out_dir=Path(tmp))
+        group_names = json.loads((Path(tmp) / "param_group_names.json").read_text())
+    assert len(groups) == len(group_names)
+    torch.save(
+        dict(kw=kw, images=images, mask_dict=mask_dict, state_dict={k: v.detach().clone() for k, v in model.state_dict().items()},
+             logits=logits, logits_masked=logits_masked, feats=feats, w=w, grads=grads, grads_masked=grads_masked,
+             lr_decay_groups=group_names, drop_scales=drop_scales),
+        OUT / f"{name}.pt",
+    )
+    print(name, {r: v.flatten()[:3].tolist() for r, v in logits.items()})
+
+
+def make_pretrain_transfer_case() -> None:
+    """MAE checkpoint -> fine-tuning model hand-off (cinema/convvit.py:616-704) on the ``mae_small_4view`` weights: which
+    keys load, the channel-tiled first stem conv for n_frames = 2, which parameters end up frozen."""
+    install_shims()
+    import tempfile
+
+    from cinema.convvit import ConvViT, load_pretrain_weights  # type: ignore
+
+    spec = CASES["mae_small_4view"]
+    mae = build_reference_mae(spec["kw"], seed=0)
+    views = ["sax", "lax_4c"]
+    kw = dict(
+        image_size_dict={v: spec["kw"]["image_size_dict"][v] for v in views}, in_chans_dict={v: 1 for v in views}, n_frames=2,
+        out_chans=2, enc_patch_size_dict={v: spec["kw"]["enc_patch_size_dict"][v] for v in views},
+        enc_scale_factor_dict={v: spec["kw"]["enc_scale_factor_dict"][v] for v in views},
+        enc_conv_chans=spec["kw"]["enc_conv_chans"], enc_conv_n_blocks=spec["kw"]["enc_conv_n_blocks"],
+        enc_embed_dim=spec["kw"]["enc_embed_dim"], enc_depth=spec["kw"]["enc_depth"], enc_n_heads=spec["kw"]["enc_n_heads"],
+    )
+    torch.manual_seed(12)
+    model = ConvViT(**kw)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "ckpt.pt"
+        torch.save({"model": mae.state_dict()}, path)
+        model = load_pretrain_weights(model, views, path, freeze=True)
+    frozen = sorted(n for n, p in model.named_parameters() if not p.requires_grad)
+    sd = model.state_dict()
+    mae_sd = mae.state_dict()
+    same_as_mae = sorted(k for k in sd if k in mae_sd and sd[k].shape == mae_sd[k].shape and torch.equal(sd[k], mae_sd[k]))
+    first = {k: sd[k].clone() for k in sd if k.endswith("conv_blocks.0.patch_embed.conv.weight")}
+    torch.save(dict(kw=kw, views=views, frozen=frozen, same_as_mae=same_as_mae, first_conv=first, keys=list(sd.keys())),
+               OUT / "convvit_transfer.pt")
+    print("convvit_transfer", len(frozen), "frozen,", len(same_as_mae), "tensors identical to the MAE checkpoint")
+
+
 def make_op_vectors() -> None:
     """Small op-level vectors from the reference functions themselves."""
     install_shims()
@@ -281,6 +421,11 @@ def main() -> None:
     for name, spec in CASES.items():
         if not only or name in only:
             make_mae_case(name, spec)
+    for name, spec in CONVVIT_CASES.items():
+        if not only or name in only:
+            make_convvit_case(name, spec)
+    if not only or "convvit_transfer" in only:
+        make_pretrain_transfer_case()
     if not only or "ops" in only:
         make_op_vectors()
 

@@ -494,3 +494,45 @@ def test_gemm_epilogue_column_sums(m, n, k):
         else:
             _C.gemm(dy, w, out2, b_mn=True)
         assert torch.equal(out, out2)  # the side output does not change the main one
+
+
+@pytest.mark.parametrize("m,n,k,rows", [(6 * 197, 768, 768, 197), (4 * 2305, 512, 256, 2305), (3 * 50, 64, 128, 50)])
+def test_gemm_row_scale_epilogue(m, n, k, rows):
+    """Stochastic depth fused into the branch's last Linear: out = residual + s[row // rows] * (A W^T + b), fp32 and bf16
+    outputs; s = 1 reproduces the plain epilogue bit for bit."""
+    a = bf16_randn(m, k, seed=4)
+    w = bf16_randn(n, k, scale=0.05, seed=5)
+    bias = torch.randn(n, device=DEV)
+    res = torch.randn(m, n, device=DEV)
+    groups = m // rows
+    s = torch.tensor([0.0, 1.0 / 0.6] * groups, device=DEV)[:groups].contiguous()
+    ref = (a.float() @ w.float().t() + bias) * s.repeat_interleave(rows)[:, None] + res
+    out = torch.empty(m, n, device=DEV)
+    _C.gemm(a, w, out, bias=bias, residual=res, row_scale=s, rows_per_group=rows)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+    dropped = (s == 0).repeat_interleave(rows)
+    assert torch.equal(out[dropped], res[dropped])  # a dropped sample passes the residual through untouched
+    out16 = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    _C.gemm(a, w, out16, bias=bias, residual=res, row_scale=s, rows_per_group=rows)
+    torch.testing.assert_close(out16.float(), ref, rtol=1e-2, atol=2e-2)
+    ones = torch.ones(groups, device=DEV)
+    o1, o2 = torch.empty(m, n, device=DEV), torch.empty(m, n, device=DEV)
+    _C.gemm(a, w, o1, bias=bias, residual=res, row_scale=ones, rows_per_group=rows)
+    _C.gemm(a, w, o2, bias=bias, residual=res)
+    assert torch.equal(o1, o2)
+
+
+def test_scale_cast_grouped():
+    """bf16(src * s[i // group]): the per-sample branch gradient of stochastic depth; scalar mode unchanged."""
+    b, n, d = 5, 37, 64
+    src = torch.randn(b * n, d, device=DEV)
+    s = torch.tensor([0.0, 2.0, 1.25, 0.0, 1.0], device=DEV)
+    dst = torch.empty(b * n, d, device=DEV, dtype=torch.bfloat16)
+    _C.scale_cast(src, dst, s, group=n * d)
+    ref = (src.view(b, -1) * s[:, None]).view(b * n, d).to(torch.bfloat16)
+    assert torch.equal(dst, ref)
+    one = torch.tensor([0.5], device=DEV)
+    _C.scale_cast(src, dst, one, scale=3.0)
+    assert torch.equal(dst, (src * 1.5).to(torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        _C.scale_cast(src, dst, s[:4].contiguous(), group=6)  # group must be a multiple of 4 dividing n

@@ -268,3 +268,113 @@ def test_full_size_vitb_matches_stock_torch_path():
                  "enc_down_dict.sax.conv_blocks.0.conv.0.dw_conv.weight", "enc_down_dict.lax_2c.patch_embed.proj.weight",
                  "enc_fusion_dict.sax.down_convs.0.weight", "encoder.cls_token"):
         assert rel(grads[name], ref_grads[name]) < 6e-2, (name, rel(grads[name], ref_grads[name]))
+
+
+# ------------------------------------------------------------------------------------------
+# ConvViT: the classification / regression fine-tuning model on the same kernels
+# ------------------------------------------------------------------------------------------
+def _convvit_oracle_autocast(g, masks):
+    cfg = O.convvit_config(g["kw"])
+    params = {k: v.to(DEV).clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = O.convvit_forward(params, cfg, _to(g["images"], DEV), None if masks is None else _to(masks, DEV), "all")
+    (out.float() * g["w"].to(DEV)).sum().backward()
+    return out.detach().float(), {k: p.grad for k, p in params.items() if p.grad is not None}
+
+
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("case", ["convvit_2view", "convvit_frames_resized"])
+def test_convvit_parity(case, masked, golden_dir):
+    """Logits (all reduce modes), features and gradients against the fp32 reference golden; yardstick = the stock torch
+    bf16-autocast path's own error (x 1.5 + floor), as for the MAE step."""
+    from cinema_b200 import ConvViT
+
+    g = torch.load(golden_dir / f"{case}.pt")
+    model = ConvViT(**g["kw"]).to(DEV)
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    images = _to(g["images"], DEV)
+    masks = g["mask_dict"] if masked else None
+    out = model(images, None if masks is None else _to(masks, DEV), "all")
+    (out * g["w"].to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    ref = (g["logits_masked"] if masked else g["logits"])["all"]
+    stock_out, stock_grads = _convvit_oracle_autocast(g, masks)
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((out.cpu() - ref).abs().max()) <= 1.5 * float((stock_out.cpu() - ref).abs().max()) + 5e-3 * scale
+    named = dict(model.named_parameters())
+    for k, ref_g in (g["grads_masked"] if masked else g["grads"]).items():
+        ours, stock = rel(named[k].grad, ref_g), rel(stock_grads[k], ref_g)
+        assert ours <= 1.5 * stock + 5e-3, (k, ours, stock)
+    if not masked:
+        model.eval()
+        with torch.no_grad():
+            feats = model.feature_forward(images, None)
+            for k, f in g["feats"].items():
+                assert rel(feats[k], f) < 3e-2, k
+            for reduce, want in g["logits"].items():
+                got = model(images, None, reduce)
+                assert float((got.cpu() - want).abs().max()) <= 3e-2 * max(1.0, float(want.abs().max())), reduce
+
+
+def test_convvit_full_size_vitb_sax_step():
+    """ViT-B ConvViT on SAX 192 x 192 x 16 (2305 tokens through the encoder, config 4's encoder shape): one training
+    step runs on the native path, logits finite and equal between two identical calls, every parameter gets a gradient."""
+    from cinema_b200 import ConvViT
+
+    torch.manual_seed(0)
+    model = ConvViT(image_size_dict={"sax": (192, 192, 16)}, in_chans_dict={"sax": 1}, n_frames=1, out_chans=4,
+                    enc_patch_size_dict={"sax": (4, 4, 1)}, enc_scale_factor_dict={"sax": (2, 2, 1)}, enc_conv_chans=[64, 128],
+                    enc_conv_n_blocks=2, enc_embed_dim=768, enc_depth=12, enc_n_heads=12).to(DEV)
+    model.train()
+    x = {"sax": torch.rand(2, 1, 192, 192, 16, device=DEV)}
+    out = model(x)
+    assert out.shape == (2, 4) and bool(torch.isfinite(out).all())
+    assert model._dense_levels == [0]
+    torch.nn.functional.cross_entropy(out, torch.tensor([1, 3], device=DEV)).backward()
+    for k, p in model.named_parameters():
+        assert (p.grad is not None) == p.requires_grad, k
+        if p.grad is not None:
+            assert bool(torch.isfinite(p.grad).all()), k
+    assert float(model.encoder.blocks[0].attn.q.weight.grad.abs().sum()) > 0
+    with torch.no_grad():
+        assert torch.equal(model(x), model(x))
+
+
+def test_convvit_stochastic_depth_parity(golden_dir, monkeypatch):
+    """drop_path > 0, training mode (every fine-tuning config of the reference): replaying the per-sample factors the
+    reference drew, logits and gradients match the fp32 golden within the stock bf16 path's own error."""
+    from cinema_b200 import ConvViT, engine
+
+    g = torch.load(golden_dir / "convvit_droppath.pt")
+    model = ConvViT(**g["kw"]).to(DEV)
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    queue = [t.to(DEV).float().contiguous() for t in g["drop_scales"]]
+    monkeypatch.setattr(engine, "draw_drop_scales", lambda b, p, k, dev: (queue.pop(0), queue.pop(0)))
+    out = model(_to(g["images"], DEV), None, "all")
+    assert not queue
+    (out * g["w"].to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    cfg = O.convvit_config(g["kw"])
+    params = {k: v.to(DEV).clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        stock = O.convvit_forward(params, cfg, _to(g["images"], DEV), None, "all",
+                                  drop_scales=[t.to(DEV) for t in g["drop_scales"]])
+    (stock.float() * g["w"].to(DEV)).sum().backward()
+    ref = g["logits"]["all"]
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((out.cpu() - ref).abs().max()) <= 1.5 * float((stock.float().cpu() - ref).abs().max()) + 5e-3 * scale
+    named = dict(model.named_parameters())
+    for k, ref_g in g["grads"].items():
+        ours, theirs = rel(named[k].grad, ref_g), rel(params[k].grad, ref_g)
+        assert ours <= 1.5 * theirs + 5e-3, (k, ours, theirs)
+    monkeypatch.undo()
+    # with the real generator: reproducible under a seed, different across seeds, identity in eval mode
+    torch.manual_seed(1)
+    a = model(_to(g["images"], DEV), None, "all")
+    torch.manual_seed(1)
+    b = model(_to(g["images"], DEV), None, "all")
+    torch.manual_seed(2)
+    c = model(_to(g["images"], DEV), None, "all")
+    assert torch.equal(a, b) and not torch.equal(a, c)

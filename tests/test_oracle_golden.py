@@ -166,3 +166,42 @@ def test_config_shapes():
     assert cfg.grid_size("sax") == (12, 12, 16) and cfg.n_patches("sax") == 2304
     assert cfg.grid_size("lax_2c") == (16, 16) and cfg.dec_patch_size("sax") == (16, 16, 1)
     assert math.prod(cfg.dec_patch_size("lax_4c")) == 256
+
+
+@pytest.mark.parametrize("case", ["convvit_2view", "convvit_frames_resized"])
+def test_convvit_oracle_matches_reference(golden_dir, case):
+    """ConvViT restatement (logits for every reduce mode, stem mask, resized input with interpolated positional table,
+    gradients) against the real reference's outputs."""
+    g = _load(golden_dir, f"{case}.pt")
+    cfg = O.convvit_config(g["kw"])
+    sd = {k: v.clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    with torch.no_grad():
+        feats = O.convvit_feature_forward(sd, cfg, g["images"], None)
+        for k, f in g["feats"].items():
+            torch.testing.assert_close(feats[k], f, **TOL)
+        for reduce, ref in g["logits"].items():
+            torch.testing.assert_close(O.convvit_forward(sd, cfg, g["images"], None, reduce), ref, **TOL)
+        torch.testing.assert_close(O.convvit_forward(sd, cfg, g["images"], g["mask_dict"], "all"),
+                                   g["logits_masked"]["all"], **TOL)
+    for masks, want in ((None, g["grads"]), (g["mask_dict"], g["grads_masked"])):
+        for p in sd.values():
+            p.grad = None
+        (O.convvit_forward(sd, cfg, g["images"], masks, "all") * g["w"]).sum().backward()
+        for k, gr in want.items():
+            torch.testing.assert_close(sd[k].grad, gr, rtol=1e-4, atol=1e-6)
+
+
+def test_convvit_oracle_stochastic_depth_matches_reference(golden_dir):
+    """Training-mode DropPath: replaying the per-sample factors the reference drew reproduces its logits and gradients."""
+    g = _load(golden_dir, "convvit_droppath.pt")
+    cfg = O.convvit_config(g["kw"])
+    sd = {k: v.clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    out = O.convvit_forward(sd, cfg, g["images"], None, "all", drop_scales=g["drop_scales"])
+    torch.testing.assert_close(out.detach(), g["logits"]["all"], **TOL)
+    (out * g["w"]).sum().backward()
+    for k, gr in g["grads"].items():
+        torch.testing.assert_close(sd[k].grad, gr, rtol=1e-4, atol=1e-6)
+    with torch.no_grad():  # eval mode: identity
+        feats = O.convvit_feature_forward(sd, cfg, g["images"], None)
+    for k, f in g["feats"].items():
+        torch.testing.assert_close(feats[k], f, **TOL)
