@@ -211,3 +211,62 @@ class MaskedConvBlock(nn.Module):
             h = mask.unsqueeze(1).to(h.dtype) * h
         x = x + self.conv2(self.dw_conv(h))
         return x + self.mlp(self.norm2(x))
+
+
+class ConvTranspose2d(nn.ConvTranspose2d):
+    """nn.ConvTranspose2d with the reference's grad-ckpt switch (cinema/conv.py:75-89); kept as an attribute only."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.grad_ckpt = False
+
+    @torch.jit.ignore
+    def set_grad_ckpt(self, enable: bool = True) -> None:
+        self.grad_ckpt = enable
+
+
+class ConvTranspose3d(nn.ConvTranspose3d):
+    """nn.ConvTranspose3d with the reference's grad-ckpt switch (cinema/conv.py:92-106); kept as an attribute only."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.grad_ckpt = False
+
+    @torch.jit.ignore
+    def set_grad_ckpt(self, enable: bool = True) -> None:
+        self.grad_ckpt = enable
+
+
+class ConvResBlock(nn.Module):
+    """x -> conv2(drop(act(norm2(conv1(act(norm1 x)))))) + shortcut(x)  (cinema/conv.py:276-346): the residual unit of
+    the segmentation decoder.  Dense k x k (x k) convolutions at up to full image resolution: cuDNN under bf16 autocast."""
+
+    def __init__(self, n_dims, in_chans, out_chans, norm, dropout: float = 0.0, kernel_size: KernelSizeType = 3,
+                 act_layer=nn.GELU) -> None:
+        if n_dims not in {2, 3}:
+            raise ValueError(f"Invalid n_dims, must be 2 or 3, got {n_dims}.")
+        if not isinstance(kernel_size, int) and len(kernel_size) != n_dims:
+            raise ValueError(f"Invalid kernel_size {kernel_size}, must be an integer or a tuple of {n_dims} integers.")
+        super().__init__()
+        self.grad_ckpt = False
+        conv_cls = Conv2d if n_dims == 2 else Conv3d
+        self.norm1 = get_conv_norm(n_dims=n_dims, in_chans=in_chans, norm=norm)
+        self.norm2 = get_conv_norm(n_dims=n_dims, in_chans=out_chans, norm=norm)
+        self.conv1 = conv_cls(in_chans, out_chans, kernel_size=kernel_size, padding="same")
+        self.conv2 = conv_cls(out_chans, out_chans, kernel_size=kernel_size, padding="same")
+        self.dropout = nn.Dropout(dropout)
+        self.act = act_layer()
+        self.shortcut = conv_cls(in_chans, out_chans, kernel_size=1) if in_chans != out_chans else nn.Identity()
+
+    @torch.jit.ignore
+    def set_grad_ckpt(self, enable: bool = True) -> None:
+        self.grad_ckpt = enable
+        self.conv1.set_grad_ckpt(enable)
+        self.conv2.set_grad_ckpt(enable)
+        if hasattr(self.shortcut, "set_grad_ckpt"):
+            self.shortcut.set_grad_ckpt(enable)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h = self.conv1(self.act(self.norm1(x)))
+        h = self.conv2(self.dropout(self.act(self.norm2(h))))
+        return h + self.shortcut(x)

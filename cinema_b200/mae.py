@@ -136,8 +136,9 @@ def _lin_of(arena, mod, train):
     return engine.linw(arena, mod.weight, mod.bias, train)
 
 
-def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32):
-    """Visible-token embedding, ViT encoder and multi-scale fusion.
+def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32, fuse=True):
+    """Visible-token embedding, ViT encoder and multi-scale fusion (``fuse=False``: stop after the encoder's final
+    LayerNorm and return (None, {"enc": (B, 1 + sum n_keep, D) fp32}, state) -- models without a fusion stage).
 
     sources[v]: per stem level a triple (src, grid, idx) such that ``gather_patches(src, grid, patch, idx, ...)`` yields
     one row per visible token -- either a dense (B, C, *spatial) map with the token grid and ``keep`` ids, or the
@@ -185,6 +186,8 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32)
     _, enc32, st.enc_mean, st.enc_rstd = engine.ln_fwd(cur, st.enc_norm, want16=False, want32=True, stats=train)
     st.enc_last = cur if train else None
     enc3 = enc32.view(b, n, d)
+    if not fuse:
+        return None, {"enc": enc3}, st
 
     total = b + b * sum(n_keeps)
     f16 = torch.empty((total, d), dtype=BF16, device=dev)
@@ -225,17 +228,19 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32)
     return f16, fused32, st
 
 
-def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets):
+def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets, fuse=True):
     """Backward of :func:`_encode` given d F (fp32, (B + B * sum n_keep, D)).  targets[v][lvl] = (dst, grid, idx) names the
     pre-zeroed gradient buffer of source level lvl (same addressing as the source) or is None when no gradient is needed;
-    contributions are accumulated into it."""
+    contributions are accumulated into it.  ``fuse=False``: ``d_f32`` is the gradient of the encoder output
+    (B, 1 + sum n_keep, D) and only the last entry of targets[v] (the embedding source) is used."""
     dev = d_f32.device
     n, d = st.n, st.d
-    denc = torch.empty((b, n, d), dtype=F32, device=dev)
-    _C.scatter_rows(d_f32[:b].view(b, 1, d), engine.arange_idx(b, 0, 1, dev), denc)
+    denc = torch.empty((b, n, d), dtype=F32, device=dev) if fuse else d_f32.contiguous()
+    if fuse:
+        _C.scatter_rows(d_f32[:b].view(b, 1, d), engine.arange_idx(b, 0, 1, dev), denc)
     idx_rows = [engine.arange_idx(b, st.offs[i], n_keeps[i], dev) for i in range(len(views))]
     vs = engine.ViewStreams(dev)
-    for i, _ in enumerate(views):
+    for i, _ in enumerate(views if fuse else []):
         nk = n_keeps[i]
         lv, nw, cur_v, mean, rstd = st.fusion[i]
         dyv = _rows(d_f32, st.foffs[i], b * nk)

@@ -571,6 +571,75 @@ def convvit_forward(sd: StateDict, cfg: MAEConfig, image_dict: dict[str, Tensor]
 
 
 # --------------------------------------------------------------------------------------
+# ConvUNetR: segmentation fine-tuning model (cinema/segmentation/convunetr.py:25-106,214-485)
+# --------------------------------------------------------------------------------------
+def conv_res_block(sd: StateDict, name: str, x: Tensor, eps: float) -> Tensor:
+    """ConvResBlock.forward (cinema/conv.py:329-346), layer norm, GELU, dropout 0, odd kernel with "same" padding."""
+    k = sd[f"{name}.conv1.weight"].shape[2:]
+    pad = tuple(kk // 2 for kk in k)
+    h = _conv(sd, f"{name}.conv1", F.gelu(conv_layer_norm(sd, f"{name}.norm1", x, eps)), padding=pad)
+    h = _conv(sd, f"{name}.conv2", F.gelu(conv_layer_norm(sd, f"{name}.norm2", h, eps)), padding=pad)
+    return h + (_conv(sd, f"{name}.shortcut", x) if f"{name}.shortcut.weight" in sd else x)
+
+
+def _deconv(sd: StateDict, name: str, x: Tensor) -> Tensor:
+    w = sd[f"{name}.weight"]  # kernel == stride (cinema/segmentation/convunetr.py:66)
+    fn = F.conv_transpose2d if x.ndim == 4 else F.conv_transpose3d
+    return fn(x, w, sd.get(f"{name}.bias"), stride=tuple(w.shape[2:]))
+
+
+def upsample_decoder(sd: StateDict, name: str, embeddings: list[Tensor | None], n_blocks: int, eps: float) -> Tensor:
+    """UpsampleDecoder.forward (cinema/segmentation/convunetr.py:88-106)."""
+    embeddings = list(embeddings)
+    x = embeddings.pop()
+    level = 0
+    while f"{name}.blocks.{level}.up.weight" in sd:
+        x = _deconv(sd, f"{name}.blocks.{level}.up", x)
+        skip = embeddings.pop()
+        if skip is not None:
+            x = x + skip
+        for j in range(n_blocks):
+            x = conv_res_block(sd, f"{name}.blocks.{level}.conv.{j}", x, eps)
+        level += 1
+    return x
+
+
+def convunetr_forward(sd: StateDict, cfg: MAEConfig, image_dict: dict[str, Tensor], n_layers_wo_skip: int,
+                      drop_scales: list[Tensor] | None = None) -> dict[str, Tensor]:
+    """ConvUNetR.forward (cinema/segmentation/convunetr.py:436-485).  ``cfg`` from :func:`convvit_config`-style arguments
+    (stem / encoder fields); the decoder structure is read off the state dict."""
+    views = list(image_dict.keys())
+    eps = cfg.conv_norm_eps
+    xs, skips_all, ns = [], [], []
+    for v in views:
+        skips, tok = downsample_encoder(sd, f"enc_down_dict.{v}", cfg, v, image_dict[v], None)
+        skips_all.append(skips), xs.append(tok), ns.append(tok.shape[1])
+    x = vit_encoder(sd, "encoder", torch.cat(xs, dim=1), cfg.enc_depth, cfg.enc_n_heads, cfg.norm_eps, cfg.rotary,
+                    drop_scales=drop_scales)
+    tokens = torch.split(x, [1, *ns], dim=1)[1:]
+    preds = {}
+    for i, v in enumerate(views):
+        grid = tuple(s // p for s, p in zip(image_dict[v].shape[2:], cfg.dec_patch_size(v)))
+        xv = tokens[i].permute(0, 2, 1).reshape(x.shape[0], x.shape[2], *grid)
+        levels = [*skips_all[i], xv]
+        j = 0
+        while f"dec_down_blocks_dict.{v}.{j}.weight" in sd:
+            w = sd[f"dec_down_blocks_dict.{v}.{j}.weight"]
+            xv = _conv(sd, f"dec_down_blocks_dict.{v}.{j}", xv, stride=tuple(w.shape[2:]))
+            levels.append(xv)
+            j += 1
+        emb: list[Tensor | None] = [conv_res_block(sd, f"dec_image_conv_block_dict.{v}", image_dict[v], eps)]
+        emb += [None] * n_layers_wo_skip
+        emb += [conv_res_block(sd, f"dec_conv_blocks_dict.{v}.{k}", lv, eps) for k, lv in enumerate(levels)]
+        preds[v] = _conv(sd, f"pred_head_dict.{v}", upsample_decoder(sd, f"decoder_dict.{v}", emb, 2, eps))
+    return preds
+
+
+def convunetr_config(kw: dict) -> MAEConfig:
+    return convvit_config({**kw, "n_frames": 1})
+
+
+# --------------------------------------------------------------------------------------
 # random state dict with the reference's key schema / shapes / init distributions
 # (cinema/vit.py:32-64, cinema/mae/mae.py:349-442).  Used for CPU-baseline timing and for
 # tests that do not need reference-identical random streams.

@@ -37,6 +37,9 @@ def install_shims() -> None:
     mae_pkg = types.ModuleType("cinema.mae")
     mae_pkg.__path__ = [str(REF / "cinema" / "mae")]
     sys.modules["cinema.mae"] = mae_pkg
+    seg_pkg = types.ModuleType("cinema.segmentation")
+    seg_pkg.__path__ = [str(REF / "cinema" / "segmentation")]
+    sys.modules["cinema.segmentation"] = seg_pkg
 
     timm = types.ModuleType("timm")
     layers = types.ModuleType("timm.layers")
@@ -357,6 +360,57 @@ def make_pretrain_transfer_case() -> None:
     print("convvit_transfer", len(frozen), "frozen,", len(same_as_mae), "tensors identical to the MAE checkpoint")
 
 
+CONVUNETR_CASE = dict(
+    # segmentation fine-tuning model (cinema/segmentation/convunetr.py:214): 3-D SAX + 2-D LAX, the decoder pyramid of
+    # the reference's ACDC config scaled down (dec_chans one level deeper than the ViT grid -> one extra down block)
+    kw=dict(
+        image_size_dict={"sax": (32, 32, 4), "lax_2c": (32, 32)}, in_chans_dict={"sax": 1, "lax_2c": 1}, out_chans=3,
+        enc_patch_size_dict={"sax": (4, 4, 1), "lax_2c": (4, 4)}, enc_scale_factor_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)},
+        enc_conv_chans=[8, 16], enc_conv_n_blocks=1, enc_embed_dim=64, enc_depth=2, enc_n_heads=2,
+        dec_chans=(4, 8, 8, 16, 16), dec_patch_size_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)},
+        dec_scale_factor_dict={"sax": (2, 2, 1), "lax_2c": (2, 2)},
+    ),
+    batch=2,
+)
+
+CONVUNETR_GRAD_KEYS = [
+    "encoder.blocks.0.attn.kv.weight", "encoder.blocks.1.mlp.fc1.bias", "encoder.cls_token", "encoder.norm.bias",
+    "enc_down_dict.sax.linear.weight", "enc_down_dict.sax.patch_embed.proj.weight",
+    "enc_down_dict.lax_2c.conv_blocks.0.patch_embed.conv.weight", "enc_down_dict.sax.conv_blocks.1.conv.0.mlp.fc2.weight",
+    "dec_down_blocks_dict.sax.0.weight", "dec_conv_blocks_dict.sax.2.conv1.weight", "dec_image_conv_block_dict.lax_2c.conv1.weight",
+    "decoder_dict.sax.blocks.0.up.weight", "pred_head_dict.sax.weight",
+]
+
+
+def make_convunetr_case() -> None:
+    install_shims()
+    from cinema.segmentation.convunetr import ConvUNetR, check_conv_unetr_enc_dec_compatiblity  # type: ignore
+
+    spec = CONVUNETR_CASE
+    kw = spec["kw"]
+    torch.manual_seed(20)
+    model = ConvUNetR(**kw)
+    model.train()
+    g = torch.Generator().manual_seed(21)
+    images = {v: torch.rand(spec["batch"], kw["in_chans_dict"][v], *s, generator=g) for v, s in kw["image_size_dict"].items()}
+    preds = model(images)
+    w = {v: torch.rand(p.shape, generator=g) for v, p in preds.items()}
+    sum((preds[v] * w[v]).sum() for v in preds).backward()
+    named = dict(model.named_parameters())
+    grads = {k: named[k].grad.clone() for k in CONVUNETR_GRAD_KEYS}
+    with torch.no_grad():
+        sax_only = model({"sax": images["sax"]})["sax"]
+    compat = {}
+    for args in [((4, 4, 1), (2, 2, 1), 2, 5, (2, 2, 1), (2, 2, 1)), ((4, 4), (2, 2), 2, 4, (2, 2), (2, 2)),
+                 ((4, 4), (2, 2), 1, 4, (1, 1), (2, 2)), ((2, 2), (2, 2), 2, 5, (1, 1), (2, 2))]:
+        compat[args] = check_conv_unetr_enc_dec_compatiblity(*args)
+    torch.save(dict(kw=kw, images=images, state_dict={k: v.detach().clone() for k, v in model.state_dict().items()},
+                    preds={k: v.detach() for k, v in preds.items()}, w=w, grads=grads, sax_only=sax_only, compat=compat,
+                    n_layers_wo_skip=model.n_layers_wo_skip),
+               OUT / "convunetr_2view.pt")
+    print("convunetr_2view", {k: tuple(v.shape) for k, v in preds.items()}, compat)
+
+
 def make_op_vectors() -> None:
     """Small op-level vectors from the reference functions themselves."""
     install_shims()
@@ -424,6 +478,8 @@ def main() -> None:
     for name, spec in CONVVIT_CASES.items():
         if not only or name in only:
             make_convvit_case(name, spec)
+    if not only or "convunetr_2view" in only:
+        make_convunetr_case()
     if not only or "convvit_transfer" in only:
         make_pretrain_transfer_case()
     if not only or "ops" in only:

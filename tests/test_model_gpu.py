@@ -378,3 +378,62 @@ def test_convvit_stochastic_depth_parity(golden_dir, monkeypatch):
     torch.manual_seed(2)
     c = model(_to(g["images"], DEV), None, "all")
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+# ------------------------------------------------------------------------------------------
+# ConvUNetR: segmentation fine-tuning model (native ViT encoder, cuDNN stem / decoder)
+# ------------------------------------------------------------------------------------------
+def test_convunetr_parity(golden_dir):
+    from cinema_b200.segmentation import ConvUNetR
+
+    g = torch.load(golden_dir / "convunetr_2view.pt")
+    model = ConvUNetR(**g["kw"]).to(DEV)
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    images, w = _to(g["images"], DEV), _to(g["w"], DEV)
+    preds = model(images)
+    sum((preds[v].float() * w[v]).sum() for v in preds).backward()
+    torch.cuda.synchronize()
+    cfg = O.convunetr_config(g["kw"])
+    params = {k: v.to(DEV).clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        stock = O.convunetr_forward(params, cfg, images, g["n_layers_wo_skip"])
+    sum((stock[v].float() * w[v]).sum() for v in stock).backward()
+    for v, ref in g["preds"].items():
+        assert preds[v].shape == ref.shape
+        ours, theirs = rel(preds[v].float(), ref), rel(stock[v].float(), ref)
+        assert ours <= 1.5 * theirs + 5e-3, (v, ours, theirs)
+    named = dict(model.named_parameters())
+    for k, ref_g in g["grads"].items():
+        ours, theirs = rel(named[k].grad, ref_g), rel(params[k].grad, ref_g)
+        assert ours <= 1.5 * theirs + 1e-2, (k, ours, theirs)
+
+
+def test_convunetr_full_size_acdc_step():
+    """BASELINE.json config 4: SAX 192 x 192 x 16, ViT-B encoder over 2305 tokens, ACDC decoder pyramid
+    (cinema/segmentation/acdc/config.yaml:41-66), 4 classes, stochastic depth 0.1: one training step, then frozen encoder."""
+    from cinema_b200.segmentation import ConvUNetR
+
+    torch.manual_seed(0)
+    model = ConvUNetR(image_size_dict={"sax": (192, 192, 16)}, in_chans_dict={"sax": 1}, out_chans=4,
+                      enc_patch_size_dict={"sax": (4, 4, 1)}, enc_scale_factor_dict={"sax": (2, 2, 1)}, enc_conv_chans=[64, 128],
+                      enc_conv_n_blocks=2, enc_embed_dim=768, enc_depth=12, enc_n_heads=12, dec_chans=(32, 64, 128, 256, 512),
+                      dec_patch_size_dict={"sax": (2, 2, 1)}, dec_scale_factor_dict={"sax": (2, 2, 1)}, drop_path=0.1).to(DEV)
+    model.train()
+    x = {"sax": torch.rand(2, 1, 192, 192, 16, device=DEV)}
+    y = torch.randint(0, 4, (2, 192, 192, 16), device=DEV)
+    out = model(x)["sax"]
+    assert out.shape == (2, 4, 192, 192, 16) and bool(torch.isfinite(out).all())
+    torch.nn.functional.cross_entropy(out.float(), y).backward()
+    for k, p in model.named_parameters():
+        assert (p.grad is not None) == p.requires_grad, k
+        if p.grad is not None:
+            assert bool(torch.isfinite(p.grad).all()), k
+    assert float(model.encoder.blocks[0].attn.q.weight.grad.abs().sum()) > 0
+    assert float(model.enc_down_dict["sax"].conv_blocks[0].patch_embed.conv.weight.grad.abs().sum()) > 0
+    model.zero_grad(set_to_none=True)
+    for p in [*model.enc_down_dict.parameters(), *model.encoder.parameters()]:
+        p.requires_grad = False
+    torch.nn.functional.cross_entropy(model(x)["sax"].float(), y).backward()
+    assert model.encoder.blocks[0].attn.q.weight.grad is None
+    assert float(model.decoder_dict["sax"].blocks[0].up.weight.grad.abs().sum()) > 0

@@ -205,3 +205,20 @@ def test_convvit_oracle_stochastic_depth_matches_reference(golden_dir):
         feats = O.convvit_feature_forward(sd, cfg, g["images"], None)
     for k, f in g["feats"].items():
         torch.testing.assert_close(feats[k], f, **TOL)
+
+
+def test_convunetr_oracle_matches_reference(golden_dir):
+    """Segmentation model restatement (stem -> encoder -> UNETR decoder) against the real reference: logits per view and
+    gradients of a weighted logit sum."""
+    g = _load(golden_dir, "convunetr_2view.pt")
+    cfg = O.convunetr_config(g["kw"])
+    sd = {k: v.clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    preds = O.convunetr_forward(sd, cfg, g["images"], g["n_layers_wo_skip"])
+    for v, ref in g["preds"].items():
+        torch.testing.assert_close(preds[v].detach(), ref, rtol=1e-4, atol=1e-5)
+    sum((preds[v] * g["w"][v]).sum() for v in preds).backward()
+    for k, gr in g["grads"].items():
+        torch.testing.assert_close(sd[k].grad, gr, rtol=2e-4, atol=1e-5)
+    with torch.no_grad():
+        out = O.convunetr_forward(sd, cfg, {"sax": g["images"]["sax"]}, g["n_layers_wo_skip"])
+    torch.testing.assert_close(out["sax"], g["sax_only"], rtol=1e-4, atol=1e-5)
