@@ -378,7 +378,11 @@ def main() -> None:
         trainer.step(resident)
 
     def step_e2e() -> None:
+        # one H2D upload of a pinned host batch and one D2H read of the loss per step, both inside the timed region; the
+        # upload of the NEXT step's batch is issued right after this step's launch so that it overlaps the compute
+        # (trainer.prefetch: copy stream + staging buffer), as a pinned-memory data loader would
         loss = trainer.step(host)
+        trainer.prefetch(host)
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the host reads this step's loss
 
@@ -386,6 +390,8 @@ def main() -> None:
         step_e2e()
     with ClockSampler(local_rank) as clocks:
         ms = timed(step_resident, args.steps)
+        if not args.skip_e2e:
+            trainer.prefetch(host)  # the first timed step's upload; every timed step issues exactly one more
         ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
     final_loss = float(loss_host[0])
     n_vol = args.batch * world * args.steps

@@ -133,11 +133,18 @@ class ConvMlp(nn.Module):
 
 
 class ConvLayerNorm(nn.LayerNorm):
-    """LayerNorm over the channel axis of a channel-first tensor (cinema/conv.py:169-187)."""
+    """LayerNorm over the channel axis of a channel-first tensor (cinema/conv.py:169-187).
+
+    The reference permutes to channel-last, normalises and copies back to NC(D)HW -- two transposes per call.  With
+    ``keep_channels_last`` the result keeps the channel-last strides it is produced with (same logical shape and values):
+    the next LayerNorm's permute is then a free view and cuDNN picks its NDHWC kernels for the convolutions in between."""
+
+    keep_channels_last = False
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = super().forward(x.movedim(1, -1))
-        return x.movedim(-1, 1).contiguous()
+        x = x.movedim(-1, 1)
+        return x if self.keep_channels_last else x.contiguous()
 
 
 def get_conv_norm(n_dims: int, in_chans: int, norm: str, eps: float = 1e-6, n_groups: int = 32) -> nn.Module:

@@ -114,7 +114,7 @@ class _EncoderFn(torch.autograd.Function):
         counts = model._dense_levels
         skips, pos = [], 0
         for c in counts:
-            skips.append([s.detach() for s in last_skips[pos:pos + c]])
+            skips.append([s.detach().contiguous() for s in last_skips[pos:pos + c]])  # the gather kernels read NC(D)HW
             pos += c
         b, dev = images[0].shape[0], images[0].device
         imgs32 = [im.detach().to(torch.float32).contiguous() for im in images]
@@ -154,7 +154,10 @@ class ConvUNetR(nn.Module):
                  enc_conv_n_blocks, enc_embed_dim, enc_depth, enc_n_heads, dec_chans, dec_patch_size_dict,
                  dec_scale_factor_dict, dec_kernel_size: int = 3, mlp_ratio: int = 4, qkv_bias: bool = True,
                  norm_layer=nn.LayerNorm, norm_eps: float = 1e-5, rotary: bool = False, act_layer=nn.GELU, mlp_layer=None,
-                 dropout: float = 0.0, drop_path: float = 0.0, norm: str = "layer") -> None:
+                 dropout: float = 0.0, drop_path: float = 0.0, norm: str = "layer", channels_last: bool = True) -> None:
+        """``channels_last`` (extension, default on): the dense stem and the decoder keep their feature maps in channel-last
+        strides between the channel LayerNorms instead of copying back to NC(D)HW after each one (see ``ConvLayerNorm``);
+        shapes, values and the state dict are unaffected."""
         super().__init__()
         self.grad_ckpt = False
         self._dense_levels: list[int] = []
@@ -204,6 +207,15 @@ class ConvUNetR(nn.Module):
                                                    scale_factor=dec_scale_factor_dict[v], norm=norm)
             self.pred_head_dict[v] = conv_cls(dec_chans[0], out_chans, kernel_size=1)
         self.apply(init_weights)
+        self.set_channels_last(channels_last)
+
+    def set_channels_last(self, enable: bool = True) -> None:
+        from cinema_b200.conv import ConvLayerNorm
+
+        self.channels_last = enable
+        for m in self.modules():
+            if isinstance(m, ConvLayerNorm):
+                m.keep_channels_last = enable
 
     @torch.jit.ignore
     def set_grad_ckpt(self, enable: bool = True) -> None:

@@ -33,6 +33,16 @@ def cosine_lr(step: float, warmup_steps: float, max_n_steps: float, lr: float, m
     return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * (step - warmup_steps) / (max_n_steps - warmup_steps)))
 
 
+def get_n_accum_steps(batch_size: int, batch_size_per_device: int, world_size: int) -> int:
+    """Gradient-accumulation factor for an effective batch size (cinema/optim.py:122-143), same checks and errors."""
+    per_step = batch_size_per_device * world_size
+    if per_step > batch_size:
+        raise ValueError(f"batch_size_per_step {per_step} should be less than batch_size {batch_size}.")
+    if batch_size % per_step != 0:
+        raise ValueError(f"batch_size {batch_size} should be divisible by batch_size_per_step {per_step}.")
+    return batch_size // per_step
+
+
 class FlatAdamW:
     """AdamW over the flat arena with global-norm clipping (cinema/mae/pretrain.py:365-367, cinema/optim.py:204-212)."""
 
@@ -74,13 +84,50 @@ class FlatAdamW:
     def grad_norm(self, grad_scale: float = 1.0) -> torch.Tensor:
         return self.gnorm_sq.sqrt() * grad_scale
 
+    def state_dict(self, names: dict[int, str] | None = None) -> dict:
+        """Optimiser state per PARAMETER NAME (layout-independent: the arena order may differ between runs / versions):
+        {"step", "exp_avg": {name: tensor}, "exp_avg_sq": {name: tensor}} -- the content of torch AdamW's state
+        (cinema/optim.py:229-260 saves ``optimizer.state_dict()``)."""
+        a = self.arena
+        names = names or a._names
+        out = {"step": self.t, "exp_avg": {}, "exp_avg_sq": {}}
+        for p in a.params:
+            if not p.requires_grad:
+                continue
+            off, n = a.offset(p), p.numel()
+            out["exp_avg"][names[id(p)]] = self.m[off:off + n].view(p.shape).clone()
+            out["exp_avg_sq"][names[id(p)]] = self.v[off:off + n].view(p.shape).clone()
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        a = self.arena
+        by_name = {a._names[id(p)]: p for p in a.params}
+        unknown = set(state["exp_avg"]) - set(by_name)
+        if unknown:
+            raise KeyError(f"optimizer state for unknown parameters: {sorted(unknown)[:5]}")
+        self.t = int(state["step"])
+        for name, t in state["exp_avg"].items():
+            p = by_name[name]
+            off, n = a.offset(p), p.numel()
+            self.m[off:off + n].copy_(t.reshape(-1))
+            self.v[off:off + n].copy_(state["exp_avg_sq"][name].reshape(-1))
+
 
 class MAETrainer:
     """One object = one rank.  ``step(batch)`` runs H2D -> forward -> backward -> all-reduce -> clip -> AdamW."""
 
     def __init__(self, model: nn.Module, *, lr: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.05,
                  clip_grad: float | None = 5.0, enc_mask_ratio: float = 0.75, use_cuda_graph: bool = True,
-                 process_group=None, graph_warmup: int = 2, overlap_allreduce: bool | None = None) -> None:
+                 process_group=None, graph_warmup: int = 2, overlap_allreduce: bool | None = None,
+                 n_accum_steps: int = 1) -> None:
+        """``n_accum_steps`` > 1: gradients of that many consecutive ``step`` calls are summed in the arena and the
+        all-reduce + clip + AdamW run on the last one with the mean (cinema/mae/pretrain.py:258-267; unlike DDP, which
+        all-reduces on every micro-step, the exchange happens once per update)."""
+        if n_accum_steps < 1:
+            raise ValueError(f"n_accum_steps must be >= 1, got {n_accum_steps}")
+        self.n_accum = n_accum_steps
+        self._micro = 0
+        self.updated = False  # did the last ``step`` call apply an optimiser update?
         self.model = model
         self.ratio = enc_mask_ratio
         self.pg = process_group
@@ -106,7 +153,7 @@ class MAETrainer:
             import os
 
             overlap_allreduce = os.environ.get("CB_OVERLAP_ALLREDUCE", "0") == "1"
-        self.overlap = self.world > 1 and overlap_allreduce and hasattr(model, "dec_linear")
+        self.overlap = self.world > 1 and overlap_allreduce and hasattr(model, "dec_linear") and self.n_accum == 1
         if self.overlap:
             from cinema_b200.mae import grad_stages
 
@@ -121,6 +168,10 @@ class MAETrainer:
         self.graph_warmup = graph_warmup
         self._n_calls = 0
         self._inputs: dict[str, torch.Tensor] | None = None
+        self._prefetched = None
+        self._copy_stream = None
+        self._staged = None
+        self._staged_free = None
         self._g_fb = self._g_opt = None
         self._loss = None
         self._loss_host = None
@@ -139,15 +190,45 @@ class MAETrainer:
         dev = self.arena.device
         if self._inputs is None:
             self._inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+        if self._prefetched is not None and self._prefetched[0] is batch:
+            # the batch was uploaded ahead of time (prefetch): one device-to-device copy into the graph's input buffers
+            _, staged, ready = self._prefetched
+            self._prefetched = None
+            torch.cuda.current_stream(dev).wait_event(ready)
+            for k, v in staged.items():
+                self._inputs[k].copy_(v, non_blocking=True)
+            self._staged_free.record(torch.cuda.current_stream(dev))
+            return
         for k, v in batch.items():
             self._inputs[k].copy_(v, non_blocking=True)
+
+    def prefetch(self, batch: dict[str, torch.Tensor]) -> None:
+        """Start the host-to-device upload of a (pinned) batch on a copy stream, so that it overlaps the step in flight;
+        the next ``step(batch)`` called with the SAME dict object consumes the uploaded copy.  The device-side role of the
+        reference's ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)`` (cinema/mae/pretrain.py:226-249)."""
+        dev = self.arena.device
+        if dev.type != "cuda":
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+            self._staged_free = torch.cuda.Event()
+            self._staged_free.record(torch.cuda.current_stream(dev))
+        ready = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._staged_free)  # the previous staged batch has been consumed
+            for k, v in batch.items():
+                self._staged[k].copy_(v, non_blocking=True)
+            ready.record(self._copy_stream)
+        self._prefetched = (batch, self._staged, ready)
 
     def _on_stage(self, stage: str) -> None:
         for s, e in self._stage_ranges.get(stage, ()):
             self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def _fwd_bwd(self) -> None:
-        self.arena.gflat.zero_()
+        if self.n_accum == 1:
+            self.arena.gflat.zero_()  # (with accumulation the first micro-step of an update clears it, outside the graph)
         self._pending = []
         loss, _, _, _ = self.model(self._inputs, self.ratio)
         loss.backward()
@@ -164,37 +245,61 @@ class MAETrainer:
             dist.all_reduce(self.arena.gflat, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _opt_apply(self) -> None:
-        self.opt.apply(grad_scale=1.0 / self.world)
+        self.opt.apply(grad_scale=1.0 / (self.world * self.n_accum))
+
+    def _begin_micro(self) -> bool:
+        """Bookkeeping of gradient accumulation; returns True when this call ends with an optimiser update."""
+        if self.n_accum > 1 and self._micro == 0:
+            self.arena.gflat.zero_()
+        self._micro = (self._micro + 1) % self.n_accum
+        self.updated = self._micro == 0
+        if self.updated:
+            self.opt.set_step_scalars()
+        return self.updated
 
     # ------------------------------------------------------------------ the step
     def step(self, batch: dict[str, torch.Tensor]) -> torch.Tensor:
         """batch: {view: (B, C, *spatial)} host (pinned) or device tensors.  Returns the loss as a 0-d DEVICE tensor
         (valid until the next call); nothing here synchronises with the host."""
         self._stage(batch)
-        self.opt.set_step_scalars()
+        update = self._begin_micro()
         if not self.use_graph or self._n_calls < self.graph_warmup:
             n0 = _C.launches
             self._fwd_bwd()
-            self._reduce()
-            self._opt_apply()
+            if update:
+                self._reduce()
+                self._opt_apply()
             self.launches_per_step = _C.launches - n0
         else:
             if self._g_fb is None:
                 self._capture()
             self._g_fb.replay()
-            self._reduce()
-            self._g_opt.replay()
+            if update:
+                self._reduce()
+                self._g_opt.replay()
         self._n_calls += 1
         return self._loss
 
     def eager_step(self, batch: dict[str, torch.Tensor]) -> torch.Tensor:
         """The same step without CUDA-graph replay (used for per-kernel instrumentation)."""
         self._stage(batch)
-        self.opt.set_step_scalars()
-        self._fwd_bwd()
-        self._reduce()
-        self._opt_apply()
+        if self._begin_micro():
+            self._fwd_bwd()
+            self._reduce()
+            self._opt_apply()
+        else:
+            self._fwd_bwd()
         return self._loss
+
+    # ------------------------------------------------------------------ checkpoint (cinema/optim.py:229-294)
+    def state_dict(self) -> dict:
+        """{"model": reference-schema state dict, "optimizer": per-name AdamW moments + step}."""
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()}, "optimizer": self.opt.state_dict()}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.model.load_state_dict(state["model"])  # the post-hook refreshes the bf16 shadow
+        self.opt.load_state_dict(state["optimizer"])
+        self._micro = 0
 
     def _capture(self) -> None:
         torch.cuda.synchronize()

@@ -110,3 +110,94 @@ def test_allreduce_buckets_partition_the_arena():
         assert bool((hit[off:off + p.numel()] == (1 if p.requires_grad else 0)).all()), arena._names[id(p)]
     # a module subtree is a handful of contiguous runs (one per optimiser category, registration-order layout)
     assert len(arena.ranges_of(stages["decoder"])) <= 3
+
+
+# ------------------------------------------------------------------------------------------
+# single-process trainer logic (kernels emulated): gradient accumulation, checkpoint round trip
+# ------------------------------------------------------------------------------------------
+def _trainer(n_accum=1, lr=1e-3):
+    from cinema_b200 import CineMA
+    from cinema_b200.train import MAETrainer
+
+    g = torch.load(GOLDEN)
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    tr = MAETrainer(model, lr=lr, use_cuda_graph=False, n_accum_steps=n_accum)
+    orig = model.forward
+    state = {"masks": None}
+    model.forward = lambda image_dict, ratio: orig(image_dict, ratio, enc_mask_dict=state["masks"])
+    return g, tr, state
+
+
+def test_gradient_accumulation_equals_full_batch_step():
+    """Two micro-steps of one sample each (n_accum_steps = 2) = one step on both samples: same mean gradient, same update
+    (cinema/mae/pretrain.py:258-267), and no optimiser update on the first micro-step."""
+    _patch()
+    g, tr_full, st_full = _trainer(1)
+    st_full["masks"] = g["masks"]
+    tr_full.step(g["images"])
+    assert tr_full.updated
+    _, tr_acc, st_acc = _trainer(2)
+    before = tr_acc.arena.flat32.clone()
+    for i in range(2):
+        st_acc["masks"] = {k: v[i:i + 1] for k, v in g["masks"].items()}
+        tr_acc.step({k: v[i:i + 1] for k, v in g["images"].items()})
+        if i == 0:
+            assert not tr_acc.updated and torch.equal(tr_acc.arena.flat32, before) and tr_acc.opt.t == 0
+    assert tr_acc.updated and tr_acc.opt.t == 1
+    # per-sample losses are means over that sample's masked patches -> the full-batch gradient is the mean of the two
+    gfull, gacc = tr_full.arena.gflat, tr_acc.arena.gflat / 2
+    assert float((gfull - gacc).norm() / gfull.norm()) < 2e-2  # bf16 rounding of different batch shapes
+    assert abs(float(tr_full.opt.grad_norm(1.0)) - float(tr_acc.opt.grad_norm(0.5))) < 2e-2 * float(tr_full.opt.grad_norm(1.0))
+    d_full, d_acc = tr_full.arena.flat32 - before, tr_acc.arena.flat32 - before
+    assert float((d_full - d_acc).norm() / d_full.norm()) < 5e-2
+    # the next update starts from a cleared accumulator
+    st_acc["masks"] = {k: v[:1] for k, v in g["masks"].items()}
+    tr_acc.step({k: v[:1] for k, v in g["images"].items()})
+    one = tr_acc.arena.gflat.clone()
+    _, tr_one, st_one = _trainer(1)
+    st_one["masks"] = st_acc["masks"]
+    tr_one.model.load_state_dict(tr_acc.model.state_dict())
+    tr_one.step({k: v[:1] for k, v in g["images"].items()})
+    assert float((one - tr_one.arena.gflat).norm() / one.norm()) < 1e-5
+
+
+def test_trainer_checkpoint_round_trip():
+    """state_dict() -> fresh trainer -> load_state_dict(): the continued run is identical to the uninterrupted one."""
+    _patch()
+    g, tr_a, st_a = _trainer(1)
+    st_a["masks"] = g["masks"]
+    for _ in range(2):
+        tr_a.step(g["images"])
+    ckpt = tr_a.state_dict()
+    assert set(ckpt) == {"model", "optimizer"} and ckpt["optimizer"]["step"] == 2
+    assert set(ckpt["optimizer"]["exp_avg"]) == {n for n, p in tr_a.model.named_parameters() if p.requires_grad}
+    tr_a.step(g["images"])
+    _, tr_b, st_b = _trainer(1)
+    st_b["masks"] = g["masks"]
+    tr_b.load_state_dict(ckpt)
+    assert tr_b.opt.t == 2
+    tr_b.step(g["images"])
+    assert torch.equal(tr_a.arena.flat32, tr_b.arena.flat32)
+    assert torch.equal(tr_a.opt.m, tr_b.opt.m) and torch.equal(tr_a.opt.v, tr_b.opt.v)
+
+
+def test_get_n_accum_steps_and_cosine_lr():
+    import math
+
+    import pytest
+
+    from cinema_b200.train import cosine_lr, get_n_accum_steps
+
+    assert get_n_accum_steps(256, 16, 8) == 2 and get_n_accum_steps(128, 16, 8) == 1
+    with pytest.raises(ValueError):
+        get_n_accum_steps(64, 16, 8)
+    with pytest.raises(ValueError):
+        get_n_accum_steps(200, 16, 8)
+    # cinema/optim.py:21-52: linear warm-up, half-cycle cosine to min_lr
+    assert cosine_lr(0, 10, 100, 1e-3, 1e-5) == 0.0
+    assert abs(cosine_lr(5, 10, 100, 1e-3, 1e-5) - 5e-4) < 1e-12
+    assert abs(cosine_lr(10, 10, 100, 1e-3, 1e-5) - 1e-3) < 1e-12
+    assert abs(cosine_lr(55, 10, 100, 1e-3, 1e-5) - (1e-5 + (1e-3 - 1e-5) * 0.5 * (1 + math.cos(math.pi * 0.5)))) < 1e-12
+    assert abs(cosine_lr(100, 10, 100, 1e-3, 1e-5) - 1e-5) < 1e-12
