@@ -584,6 +584,18 @@ class _MAEFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *flat)
 
 
+class _DirectCtx:
+    """Stand-in for the autograd context when ``_MAEFn.forward`` / ``backward`` are called directly (train_step)."""
+
+    needs_input_grad = (False, False, False, False, False, True)  # the parameter anchor
+
+    def __init__(self) -> None:
+        self.state = None
+
+    def mark_non_differentiable(self, *_):
+        pass
+
+
 # ------------------------------------------------------------------------------------------
 # the module
 # ------------------------------------------------------------------------------------------
@@ -742,6 +754,41 @@ class CineMA(nn.Module):
                 metrics[f"{v}_pred_max"] = out[5 + 5 * i]
         metrics["loss"] = loss
         return loss, dict(zip(views, preds)), dict(zip(views, masks)), metrics
+
+    def direct_step_supported(self) -> bool:
+        """Can :meth:`train_step` be used (every stem runs natively, at least one trainable parameter)?"""
+        return (self.native_stem and all(stem.supported(self.enc_down_dict[v]) for v in self.views)
+                and any(p.requires_grad for p in self.parameters()))
+
+    @torch.no_grad()
+    def train_step(self, image_dict: dict[str, torch.Tensor], enc_mask_ratio: float,
+                   enc_mask_dict: dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+        """forward + backward of ``forward(image_dict, enc_mask_ratio)[0]`` without the autograd engine: the fused
+        forward and its hand-written backward are called back to back on the calling thread (same kernels, same RNG
+        draws, gradients accumulated into the ``.grad`` arena views).  Returns the detached loss.  This is what
+        ``MAETrainer`` runs: with no engine thread in between, the step can be captured as SEVERAL CUDA graphs split at
+        the gradient stages (``_grad_stage_done``), which is how the gradient all-reduce overlaps the backward."""
+        if not self.direct_step_supported():
+            raise RuntimeError("train_step needs the native stem for every view and a trainable parameter")
+        views = self._check_views(image_dict)
+        first = image_dict[views[0]]
+        b, dev = first.shape[0], first.device
+        masks, n_keeps = [], []
+        for v in views:
+            down = self.enc_down_dict[v]
+            grid = tuple(s // p for s, p in zip(image_dict[v].shape[2:], down.eff_patch_size))
+            n_patches = math.prod(grid)
+            if enc_mask_dict is not None:  # given masks (tests / comparisons), as in forward()
+                masks.append(enc_mask_dict[v].to(device=dev, dtype=torch.bool))
+                n_keeps.append(n_patches - int(masks[-1][0].sum()))
+            else:
+                masks.append(get_batch_random_patch_mask(b, n_patches, enc_mask_ratio, dev))
+                n_keeps.append(n_patches if enc_mask_ratio == 0 else int(n_patches * (1 - enc_mask_ratio)))
+        self._dense_levels = [0] * len(views)
+        ctx = _DirectCtx()
+        loss, *_ = _MAEFn.forward(ctx, self, views, [image_dict[v] for v in views], masks, n_keeps, None)
+        _MAEFn.backward(ctx, torch.ones((), dtype=F32, device=dev), None)
+        return loss
 
     @classmethod
     def from_pretrained(cls, config: dict | None = None, state_dict: dict | None = None, **kwargs) -> "CineMA":

@@ -149,11 +149,16 @@ class MAETrainer:
         self._stage_ranges: dict[str, list[tuple[int, int]]] = {}
         self._rest_ranges: list[tuple[int, int]] = [(0, self.arena.numel)]
         self._pending: list = []
-        if overlap_allreduce is None:  # opt-in for now (CB_OVERLAP_ALLREDUCE=1): see DESIGN.md section 7
-            import os
+        import os
 
-            overlap_allreduce = os.environ.get("CB_OVERLAP_ALLREDUCE", "0") == "1"
-        self.overlap = self.world > 1 and overlap_allreduce and hasattr(model, "dec_linear") and self.n_accum == 1
+        # forward + backward without the autograd engine (CineMA.train_step) when the model supports it
+        self._direct = bool(getattr(model, "direct_step_supported", lambda: False)()) and os.environ.get("CB_DIRECT_STEP", "1") == "1"
+        if overlap_allreduce is None:  # CB_OVERLAP_ALLREDUCE=0 turns the bucketed overlap off
+            overlap_allreduce = os.environ.get("CB_OVERLAP_ALLREDUCE", "1") == "1" and self._direct
+        # CB_FORCE_SPLIT=1: split the step's graph at the gradient stages even on one rank (tests of the capture logic)
+        self._force_split = os.environ.get("CB_FORCE_SPLIT", "0") == "1"
+        self.overlap = ((self.world > 1 or self._force_split) and overlap_allreduce and hasattr(model, "dec_linear")
+                        and self.n_accum == 1)
         if self.overlap:
             from cinema_b200.mae import grad_stages
 
@@ -173,6 +178,9 @@ class MAETrainer:
         self._staged = None
         self._staged_free = None
         self._g_fb = self._g_opt = None
+        self._fb_segments: list = []  # [(graph, flat ranges to all-reduce once it has run)] when the capture is split
+        self._capturing = False
+        self._cur_graph = None
         self._loss = None
         self._loss_host = None
         self.launches_per_step = 0
@@ -222,23 +230,60 @@ class MAETrainer:
             ready.record(self._copy_stream)
         self._prefetched = (batch, self._staged, ready)
 
-    def _on_stage(self, stage: str) -> None:
-        for s, e in self._stage_ranges.get(stage, ()):
-            self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+    def _reduce_async(self, ranges) -> None:
+        """Hand flat gradient ranges to NCCL on its own stream (ordered after everything queued on the current stream so
+        far); the caller joins with ``_join_reduces`` before the optimiser reads the gradients."""
+        if self.world > 1:
+            for s, e in ranges:
+                self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
-    def _fwd_bwd(self) -> None:
+    def _join_reduces(self) -> None:
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+    def _on_stage(self, stage: str) -> None:
+        """Called by the model in the middle of the backward when a parameter subtree's gradients are final."""
+        ranges = self._stage_ranges.get(stage, ())
+        if self._capturing:
+            # end the current graph here and continue the capture in a new one: at replay time the all-reduce of this
+            # stage is launched between the two graphs and overlaps the second one -- no NCCL call is ever captured
+            g = self._cur_graph
+            g.capture_end()
+            self._fb_segments.append((g, ranges))
+            g2 = torch.cuda.CUDAGraph()
+            g2.capture_begin(pool=self._fb_segments[0][0].pool())
+            self._cur_graph = g2
+        else:
+            self._reduce_async(ranges)
+
+    def _compute(self) -> None:
+        """Forward + backward into the gradient arena; the stage hooks fire inside."""
         if self.n_accum == 1:
             self.arena.gflat.zero_()  # (with accumulation the first micro-step of an update clears it, outside the graph)
+        if self._direct:
+            self._loss = self.model.train_step(self._inputs, self.ratio)
+        else:
+            loss, _, _, _ = self.model(self._inputs, self.ratio)
+            loss.backward()
+            self._loss = loss.detach()
+
+    def _fwd_bwd(self) -> None:
         self._pending = []
-        loss, _, _, _ = self.model(self._inputs, self.ratio)
-        loss.backward()
-        self._loss = loss.detach()
+        self._compute()
         if self.overlap:  # the rest of the arena, then join every bucket before the optimiser reads the gradients
-            for s, e in self._rest_ranges:
-                self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-            for w in self._pending:
-                w.wait()
-            self._pending = []
+            self._reduce_async(self._rest_ranges)
+            self._join_reduces()
+
+    def _replay_fwd_bwd(self) -> None:
+        if not self._fb_segments:
+            self._g_fb.replay()
+            return
+        self._pending = []
+        for g, ranges in self._fb_segments:
+            g.replay()
+            self._reduce_async(ranges)
+        self._join_reduces()
 
     def _reduce(self) -> None:
         if self.world > 1 and not self.overlap:
@@ -273,7 +318,7 @@ class MAETrainer:
         else:
             if self._g_fb is None:
                 self._capture()
-            self._g_fb.replay()
+            self._replay_fwd_bwd()
             if update:
                 self._reduce()
                 self._g_opt.replay()
@@ -291,6 +336,32 @@ class MAETrainer:
             self._fwd_bwd()
         return self._loss
 
+    def _capture_split(self) -> None:
+        """Capture forward + backward as a chain of CUDA graphs cut at the gradient stages (decoder subtree final, upper
+        encoder half final, rest).  ``train_step`` runs on this thread, so ``_on_stage`` can end one capture and begin
+        the next on the same stream; all graphs share one memory pool and are always replayed in capture order."""
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        dev = self.arena.device
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        self._fb_segments = []
+        with torch.cuda.stream(stream):
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin()
+            self._cur_graph, self._capturing = g, True
+            try:
+                self._compute()
+            finally:
+                self._capturing = False
+                self._cur_graph.capture_end()
+            self._fb_segments.append((self._cur_graph, self._rest_ranges))
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        self._cur_graph = None
+        self._g_fb = self._fb_segments[0][0]
+
     # ------------------------------------------------------------------ checkpoint (cinema/optim.py:229-294)
     def state_dict(self) -> dict:
         """{"model": reference-schema state dict, "optimizer": per-name AdamW moments + step}."""
@@ -303,9 +374,12 @@ class MAETrainer:
 
     def _capture(self) -> None:
         torch.cuda.synchronize()
-        self._g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_fb):
-            self._fwd_bwd()
+        if self.overlap and self._direct:
+            self._capture_split()
+        else:
+            self._g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_fb):
+                self._fwd_bwd()
         self._g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
             self._opt_apply()

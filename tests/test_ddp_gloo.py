@@ -35,8 +35,9 @@ def _one_step(images, masks, world):
     model.train()
     tr = MAETrainer(model, lr=1e-3, use_cuda_graph=False, overlap_allreduce=True)  # bucketed path (no-op at world 1)
     # fixed masks so that both layouts see the same problem
-    orig = model.forward
+    orig, orig_ts = model.forward, model.train_step
     model.forward = lambda image_dict, ratio: orig(image_dict, ratio, enc_mask_dict=masks)
+    model.train_step = lambda image_dict, ratio: orig_ts(image_dict, ratio, enc_mask_dict=masks)
     loss = tr.step(images)
     return float(loss), tr.arena.flat32.clone(), float(tr.opt.grad_norm(1.0 / world)), tr.arena.gflat.clone() / world
 
@@ -124,9 +125,10 @@ def _trainer(n_accum=1, lr=1e-3):
     model.load_state_dict(g["state_dict"])
     model.train()
     tr = MAETrainer(model, lr=lr, use_cuda_graph=False, n_accum_steps=n_accum)
-    orig = model.forward
+    orig, orig_ts = model.forward, model.train_step
     state = {"masks": None}
     model.forward = lambda image_dict, ratio: orig(image_dict, ratio, enc_mask_dict=state["masks"])
+    model.train_step = lambda image_dict, ratio: orig_ts(image_dict, ratio, enc_mask_dict=state["masks"])
     return g, tr, state
 
 

@@ -466,7 +466,6 @@ def test_trainer_prefetch_equals_direct_upload(golden_dir):
                 tr.prefetch(batches[i + 1])
             out.append(float(loss))
         losses[mode] = out
-    assert losses["direct"][:2] == losses["prefetch"][:2]  # eager steps: bit-identical
     assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(losses["direct"], losses["prefetch"]))  # atomics reorder sums
     assert len(set(losses["direct"])) == len(batches)  # the batches really differ
 
@@ -498,3 +497,27 @@ def test_other_baseline_configs_train(name):
     assert all(math.isfinite(x) for x in losses), losses
     assert losses[-1] < losses[0], losses
     assert tr.use_graph and tr._g_fb is not None
+
+
+def test_trainer_split_graph_equals_single_graph(golden_dir, monkeypatch):
+    """The step captured as a CHAIN of CUDA graphs cut at the gradient stages (how the gradient all-reduce overlaps the
+    backward on several GPUs; forced here on one rank) replays to the same losses and parameters as the single graph."""
+    from cinema_b200.train import MAETrainer
+
+    g = torch.load(golden_dir / "mae_small_4view.pt")
+    images = _to(g["images"], DEV)
+    out = {}
+    for split in (False, True):
+        monkeypatch.setenv("CB_FORCE_SPLIT", "1" if split else "0")
+        torch.manual_seed(0)
+        model = CineMA(**g["kw"]).to(DEV)
+        model.load_state_dict(g["state_dict"])
+        model.train()
+        tr = MAETrainer(model, lr=1e-3, use_cuda_graph=True, graph_warmup=2)
+        assert tr._direct and tr.overlap == split
+        torch.manual_seed(1)
+        losses = [float(tr.step(images)) for _ in range(6)]
+        assert len(tr._fb_segments) == (3 if split else 0)
+        out[split] = (losses, tr.arena.flat32.clone())
+    assert all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(out[True][0], out[False][0]))  # atomics reorder fp32 sums
+    assert rel(out[True][1], out[False][1]) < 1e-3

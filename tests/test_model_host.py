@@ -186,3 +186,30 @@ def test_vit_encoder_decoder_modules(golden_dir, emulated_kernels):
     att = model.encoder.blocks[1].attn
     xa = torch.randn(2, 7, kw["enc_embed_dim"], generator=gen)
     assert rel(att(xa), O.attention(sd, "encoder.blocks.1.attn", xa, None, kw["enc_n_heads"])) < 2e-2
+
+
+def test_direct_train_step_equals_autograd_step(golden_dir, emulated_kernels):
+    """``CineMA.train_step`` (forward + hand-written backward called back to back, no autograd engine) leaves the same
+    loss and the same gradients as ``forward(...)[0].backward()``."""
+    g = torch.load(golden_dir / "mae_small_4view.pt")
+    grads = {}
+    for mode in ("autograd", "direct"):
+        model = CineMA(**g["kw"])
+        model.load_state_dict(g["state_dict"])
+        model.train()
+        assert model.direct_step_supported()
+        if mode == "autograd":
+            loss, *_ = model(g["images"], g["ratio"], enc_mask_dict=g["masks"])
+            loss.backward()
+        else:
+            loss = model.train_step(g["images"], g["ratio"], enc_mask_dict=g["masks"])
+            assert not loss.requires_grad
+        grads[mode] = (float(loss), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert grads["autograd"][0] == grads["direct"][0]
+    assert set(grads["autograd"][1]) == set(grads["direct"][1])
+    for k, ref in grads["autograd"][1].items():
+        assert torch.equal(grads["direct"][1][k], ref), k
+    model.native_stem = False
+    assert not model.direct_step_supported()
+    with pytest.raises(RuntimeError):
+        model.train_step(g["images"], g["ratio"])
