@@ -254,6 +254,7 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets, fuse=True):
                     _C.scatter_patches(dpf, tgt[0], tgt[1], k, tgt[2], False, accumulate=True)
     vs.join()
     ew = st.enc_w
+    stage_points = set(encoder_stage_points(len(ew)))
     gb_of = lambda j: engine.out_bias_of(ew, j, d)  # noqa: E731
     dx32, dx16 = engine.ln_bwd(denc.view(b * n, d), st.enc_last, st.enc_mean, st.enc_rstd, st.enc_norm,
                                dxsum=gb_of(len(ew) - 1))
@@ -261,8 +262,8 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets, fuse=True):
         dx32, dx16 = engine.block_bwd(dx32, dx16, ew[j], b, st.enc_saved[j], None, None,
                                       fc2_bias_done=gb_of(j) is not None, out_bias=gb_of(j - 1))
         st.enc_saved[j] = None
-        if j == len(ew) // 2 and j > 0:
-            _grad_stage_done(model, "encoder_hi")  # encoder.norm and blocks[depth // 2:] are final
+        if j in stage_points:
+            _grad_stage_done(model, f"encoder_{j}")  # blocks[j:] (and, at the first point, encoder.norm + fusion) are final
     dx0 = dx32.view(b, n, d)
     cls = model.encoder.cls_token
     if cls.requires_grad:
@@ -290,15 +291,27 @@ def _grad_stage_done(model, stage: str) -> None:
         hook(stage)
 
 
+def encoder_stage_points(depth: int) -> list[int]:
+    """Encoder block indices (descending) after whose backward a gradient stage is reported: quarters of the stack."""
+    return sorted({depth * 3 // 4, depth // 2, depth // 4} - {0}, reverse=True)
+
+
 def grad_stages(model) -> dict[str, list[nn.Parameter]]:
-    """Parameter sets whose gradients become final at the two points reported by :func:`_grad_stage_done`."""
-    dec = [*model.dec_linear.parameters(), *model.dec_embed_dict.parameters(), *model.decoder.parameters(),
-           *model.pred_head_dict.parameters()]
+    """Parameter sets whose gradients become final at the points reported by :func:`_grad_stage_done`, in the order the
+    backward reaches them: "decoder" (decoder-side subtree), then "encoder_k" = encoder blocks [k, previous point) -- the
+    first one also carries ``encoder.norm`` and the fusion modules, whose backward has run by then.  Everything else
+    (lowest blocks, cls token, stems, embeddings) is final only when the backward ends."""
+    stages = {"decoder": [*model.dec_linear.parameters(), *model.dec_embed_dict.parameters(), *model.decoder.parameters(),
+                          *model.pred_head_dict.parameters()]}
     blocks = list(model.encoder.blocks)
-    hi = [*model.encoder.norm.parameters()]
-    for blk in blocks[len(blocks) // 2:]:
-        hi += list(blk.parameters())
-    return {"decoder": dec, "encoder_hi": hi if len(blocks) // 2 > 0 else []}
+    prev = len(blocks)
+    for k in encoder_stage_points(len(blocks)):
+        ps = [p for blk in blocks[k:prev] for p in blk.parameters()]
+        if prev == len(blocks):
+            ps += [*model.encoder.norm.parameters(), *model.enc_fusion_dict.parameters()]
+        stages[f"encoder_{k}"] = ps
+        prev = k
+    return stages
 
 
 def _needs(flags, counts):
