@@ -159,6 +159,9 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32,
         down = model.enc_down_dict[v]
         nk = n_keeps[i]
         offs.append(off)
+        if nk == 0:  # a view without any visible token contributes nothing to the encoder (tiny grids / high ratios)
+            st.embed.append(None)
+            continue
         ps = tuple(down.patch_sizes[-1])
         src, sgrid, sidx = sources[i][-1]
         e_in = src.shape[1] * math.prod(ps)
@@ -203,6 +206,11 @@ def _encode(model, arena, views, sources, keep, n_keeps, b, train, want_fused32,
         fus = model.enc_fusion_dict[v]
         nk = n_keeps[i]
         foffs.append(foff)
+        if nk == 0:
+            st.fusion.append(None)
+            if want_fused32:
+                fused32[v] = torch.empty((b, 0, d), dtype=F32, device=dev)
+            continue
         nw = engine.normw(arena, fus.norm, train)
         wcs = [_lin_of(arena, conv, train) for conv in fus.down_convs]
         with vs.view(i):  # views write disjoint row segments of f16
@@ -242,6 +250,8 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets, fuse=True):
     vs = engine.ViewStreams(dev)
     for i, _ in enumerate(views if fuse else []):
         nk = n_keeps[i]
+        if st.fusion[i] is None:
+            continue
         lv, nw, cur_v, mean, rstd = st.fusion[i]
         dyv = _rows(d_f32, st.foffs[i], b * nk)
         with vs.view(i):  # disjoint rows of denc, per-view parameters and gradient targets
@@ -270,6 +280,8 @@ def _encode_bwd(model, arena, views, st, d_f32, n_keeps, b, targets, fuse=True):
         _C.colsum_seg(dx0, 0, 1, arena.grad_view(cls).view(-1))
     for i, _ in enumerate(views):
         nk = n_keeps[i]
+        if st.embed[i] is None:
+            continue
         p16, t1, w_pe, w_li, ps = st.embed[i]
         with vs.view(i):  # left open on purpose: the caller continues with the stem backward of view i, then joins
             dt2 = torch.empty((b, nk, d), dtype=BF16, device=dev)
@@ -331,6 +343,10 @@ def _build_sources(model, arena, views, imgs32, skips, keep, masks, slot, grids,
         down = model.enc_down_dict[v]
         src = _Sources()
         src.token_grid = grids[i]
+        if n_keeps[i] == 0:  # nothing of this view is visible: no stem, no sources
+            stems.append(None)
+            sources.append(src)
+            continue
         if len(down.conv_blocks) == 0:
             src.append((imgs32[i], grids[i], keep[i]))
             stems.append(None)
@@ -367,6 +383,9 @@ def _build_targets(views, sources, stems, skips, needs):
             for lw, (src, _, _) in zip(levels, sources[i]):
                 buf = torch.zeros((t * math.prod(lw.f), lw.chans), dtype=F32, device=src.device)
                 per_view.append((stem.level_view(buf, t, lw.f), unit, None, buf))
+        elif skips[i] and len(sources[i]) == 0:  # dense maps of a view without visible tokens: no gradient
+            per_view = [None] * len(skips[i])
+            grads = [None] * len(skips[i])
         elif skips[i]:
             for lvl, sk in enumerate(skips[i]):
                 if needs[i][lvl]:
@@ -423,6 +442,8 @@ class _MAEFn(torch.autograd.Function):
 
         nk_tot, nm_tot = sum(n_keeps), sum(n_masks)
         cross = model.cross_attn
+        if cross and nk_tot == 0:
+            raise ValueError("no visible token in any view: the cross-attention decoder has no keys (lower enc_mask_ratio)")
         nq = 1 + nm_tot if cross else 1 + nk_tot + nm_tot
         xq = torch.empty((b, nq, dd), dtype=F32, device=dev)
         xk16 = torch.empty((b, nk_tot, dd), dtype=BF16, device=dev) if cross else None
@@ -437,11 +458,12 @@ class _MAEFn(torch.autograd.Function):
             nk, nm = n_keeps[i], n_masks[i]
             yv = _rows(y, st.foffs[i], b * nk).view(b, nk, dd)
             q0 = (1 + moff) if cross else (1 + nk_tot + moff)
-            if cross:
+            if nk > 0 and cross:
                 _C.embed_rows(yv, 0, None, dpos, keep[i], b, nk, out16=xk16, out_off=koff)
-            else:
+            elif nk > 0:
                 _C.embed_rows(yv, 0, None, dpos, keep[i], b, nk, out=xq, out_off=1 + koff)
-            _C.embed_rows(None, 0, emb.mask_token.data.view(-1), dpos, drop[i], b, nm, out=xq, out_off=q0)
+            if nm > 0:
+                _C.embed_rows(None, 0, emb.mask_token.data.view(-1), dpos, drop[i], b, nm, out=xq, out_off=q0)
             koffs.append(koff), qoffs.append(q0)
             koff += nk
             moff += nm
@@ -576,9 +598,9 @@ class _MAEFn(torch.autograd.Function):
         for i, v in enumerate(views):
             nk, nm = n_keeps[i], n_masks[i]
             seg = _rows(dy16, st.foffs[i], b * nk).view(b, nk, dd)
-            if cross:
+            if nk > 0 and cross:
                 _C.gather_rows(dxk3, engine.arange_idx(b, s["koffs"][i], nk, dev), seg)
-            else:
+            elif nk > 0:
                 _C.embed_rows(dxq, 1 + s["koffs"][i], None, None, None, b, nk, out16=seg)
             mt = model.dec_embed_dict[v].mask_token
             if mt.requires_grad and nm > 0:

@@ -213,3 +213,58 @@ def test_direct_train_step_equals_autograd_step(golden_dir, emulated_kernels):
     assert not model.direct_step_supported()
     with pytest.raises(RuntimeError):
         model.train_step(g["images"], g["ratio"])
+
+
+@pytest.mark.parametrize(("name", "views", "ratio", "batch"), [
+    ("subset_of_views", ["lax_3c", "sax"], 0.75, 2),  # any subset, any order (cinema/mae/mae.py:521-523)
+    ("batch_of_one", ["sax", "lax_2c", "lax_3c", "lax_4c"], 0.75, 1),
+    ("single_2d_view", ["lax_4c"], 0.5, 2),
+    # tiny grids at a high ratio: int(16 * 0.05) = 0 visible LAX tokens, 1 visible SAX token -- the reference's own tests
+    # reach this corner (cinema/mae/mae_test.py:35-66, ratio 0.9 on 2..8-token grids)
+    ("view_without_visible_tokens", ["sax", "lax_2c"], 0.95, 2),
+])
+def test_mae_edge_cases_against_oracle(name, views, ratio, batch, golden_dir, emulated_kernels):
+    from oracle import cinema_oracle as O
+
+    g = torch.load(golden_dir / "mae_small_4view.pt")
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    images = {v: g["images"][v][:batch] for v in views}
+    torch.manual_seed(7)
+    loss, preds, masks, metrics = model(images, ratio)
+    loss.backward()
+    sd = {k: v.clone().requires_grad_(not k.endswith("pos_embed")) for k, v in g["state_dict"].items()}
+    ref_loss, ref_preds, _ = O.mae_forward(sd, O.MAEConfig(**g["kw"]), images, masks)
+    ref_loss.backward()
+    assert list(preds) == views
+    assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss))
+    for v in views:
+        n = masks[v].shape[1]
+        n_keep = int(n * (1 - ratio))
+        assert ((~masks[v]).sum(1) == n_keep).all()
+        assert preds[v].shape == ref_preds[v].shape == (batch, n - n_keep, 256)
+        assert rel(preds[v], ref_preds[v]) < 3e-2, v
+    named = dict(model.named_parameters())
+    checked = 0
+    for k, p in sd.items():
+        if p.grad is None or float(p.grad.norm()) < 1e-6:  # unused views / analytically zero gradients (one-key softmax)
+            assert named[k].grad is None or float(named[k].grad.norm()) < 1e-6 or not k.startswith(("enc_", "dec_embed", "pred_head")), k
+            continue
+        assert rel(named[k].grad, p.grad) < 4e-2, (k, rel(named[k].grad, p.grad))
+        checked += 1
+    assert checked > 50
+
+
+def test_mask_ratio_zero_and_no_keys(golden_dir, emulated_kernels):
+    """enc_mask_ratio = 0: nothing to reconstruct -- empty predictions and a NaN loss, like the reference
+    (cinema/mae/mae.py:604-608); no visible token at all with a cross-attention decoder is rejected."""
+    g = torch.load(golden_dir / "mae_small_4view.pt")
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        loss, preds, masks, metrics = model(g["images"], 0.0)
+    assert math.isnan(float(loss)) and all(p.shape[1] == 0 for p in preds.values()) and not any(m.any() for m in masks.values())
+    assert all(math.isfinite(float(metrics[f"{v}_target_mean"])) for v in preds)
+    with pytest.raises(ValueError):
+        model({"lax_2c": g["images"]["lax_2c"]}, 0.99)  # int(16 * 0.01) = 0 visible tokens in the only view
