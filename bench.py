@@ -323,7 +323,7 @@ def main() -> None:
         sample_b = 2 if args.steps + args.warmup <= 30 else 1
         cpu = cpu_reference_throughput(kw, sample_b, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "mae_pretrain_volumes_per_sec", "value": cpu["value"], "unit": "frame-set volumes/s",
-                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {**config, "batch_per_gpu": sample_b, "global_batch": sample_b, "parallelism": "cpu"},
                 "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
