@@ -521,3 +521,30 @@ def test_trainer_split_graph_equals_single_graph(golden_dir, monkeypatch):
         out[split] = (losses, tr.arena.flat32.clone())
     assert all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(out[True][0], out[False][0]))  # atomics reorder fp32 sums
     assert rel(out[True][1], out[False][1]) < 1e-3
+
+
+def test_device_feeder_on_cuda_matches_host_computation(tmp_path):
+    """Input pipeline (cinema_b200/data.py): raw integer batches uploaded on the copy stream and scaled on the device equal
+    the host-side ScaleIntensity of the same frames, batch after batch (double-buffered slots are not overwritten early)."""
+    import numpy as np
+
+    from cinema_b200 import data as D
+
+    rng = np.random.default_rng(0)
+    subjects = [(f"s{i}", {"sax": rng.integers(0, 3000, size=(40, 48, 6, 4)).astype(np.int16),
+                           "lax_4c": rng.integers(0, 256, size=(56, 60, 4)).astype(np.uint8)}) for i in range(9)]
+    D.write_shards(tmp_path, subjects)
+    ds = D.CineShardDataset(tmp_path)
+    sizes = {"sax": (48, 48, 8), "lax_4c": (64, 64)}
+    mk = lambda pin: D.FrameBatcher(ds, D.ShardSampler(len(ds), seed=1), 2, sizes, n_frames=4, seed=3, pin_memory=pin)  # noqa: E731
+    host = [{v: D.scale_intensity(r.images[v], r.lo[v], r.hi[v]).clone() for v in r.images} for r in mk(False)]
+    feeder = D.DeviceFeeder(mk(True), DEV)
+    got = []
+    for batch in feeder:
+        assert all(t.is_cuda and t.dtype == torch.float32 for t in batch.values())
+        got.append({v: t.clone() for v, t in batch.items()})
+    torch.cuda.synchronize()
+    assert len(got) == len(host) == 4 and feeder.h2d_bytes_per_batch == 2 * (48 * 48 * 8 * 2 + 64 * 64) + 4 * 2 * 4
+    for a, b in zip(host, got):
+        for v in a:
+            torch.testing.assert_close(b[v].cpu(), a[v], rtol=1e-6, atol=1e-7)
