@@ -95,7 +95,7 @@ class CineShardDataset:
         arr = self._maps.get(key)
         if arr is None:
             arr = np.load(self.root / meta["file"], mmap_mode="r")
-            if len(self._maps) > 4096:
+            if len(self._maps) >= 256:  # every map holds a file descriptor: stay far below the usual 1024 limit
                 self._maps.clear()
             self._maps[key] = arr
         return arr[t], meta["frame_min"][t], meta["frame_max"][t]
