@@ -189,6 +189,9 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
     """q (B, Nq, H, d), k/v (B, Nk, H, d) strided bf16 views -> o (B, Nq, H, d) bf16 contiguous, lse (B, H, Nq)."""
     b, nq, h, d = q.shape
     check_head_dim(d)
+    if k.shape[1] == 0:  # no keys (every token of every view masked away): softmax over nothing, the output is 0
+        return (torch.zeros((b, nq, h, d), dtype=BF16, device=q.device),
+                torch.full((b, h, nq), float("-inf"), dtype=F32, device=q.device))
     o = torch.empty((b, nq, h, d), dtype=BF16, device=q.device)
     lse = torch.empty((b, h, nq), dtype=F32, device=q.device)
     _C.attention_fwd(q, k, v, o, lse, scale)
@@ -197,6 +200,9 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
 
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, scale: float) -> None:
     b, nq, h, d = q.shape
+    if k.shape[1] == 0:  # no keys: the output did not depend on q (and there is no k / v to differentiate)
+        dq.zero_()
+        return
     delta, dq_acc = _C.attention_bwd_workspace(b, h, nq, d, q.device)
     _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale)
 

@@ -442,8 +442,6 @@ class _MAEFn(torch.autograd.Function):
 
         nk_tot, nm_tot = sum(n_keeps), sum(n_masks)
         cross = model.cross_attn
-        if cross and nk_tot == 0:
-            raise ValueError("no visible token in any view: the cross-attention decoder has no keys (lower enc_mask_ratio)")
         nq = 1 + nm_tot if cross else 1 + nk_tot + nm_tot
         xq = torch.empty((b, nq, dd), dtype=F32, device=dev)
         xk16 = torch.empty((b, nk_tot, dd), dtype=BF16, device=dev) if cross else None
@@ -478,7 +476,11 @@ class _MAEFn(torch.autograd.Function):
             xk2 = xk16.view(b * nk_tot, dd)
             kv_w = engine.linw_fused(arena, [blk.attn.kv.weight for blk in model.decoder.blocks],
                                      [blk.attn.kv.bias for blk in model.decoder.blocks], train)
-            if kv_w is not None:
+            if nk_tot == 0:  # no visible token anywhere: attention over no keys returns 0 (engine.attn_fwd)
+                kv_w = None
+                kv_all = [torch.empty((b, 0, 2, h, hd), dtype=BF16, device=dev) for _ in dec_w]
+                kvs = [(t[:, :, 0], t[:, :, 1]) for t in kv_all]
+            elif kv_w is not None:
                 kv_all = engine.linear_fwd(xk2, kv_w).view(b, nk_tot, depth, 2, h, hd)
                 kvs = [(kv_all[:, :, j, 0], kv_all[:, :, j, 1]) for j in range(depth)]
             else:
@@ -579,7 +581,9 @@ class _MAEFn(torch.autograd.Function):
         total = b + b * nk_tot
         dy16 = torch.empty((total, dd), dtype=BF16, device=dev)
         _C.embed_rows(dxq, 0, None, None, None, b, 1, out16=dy16[:b].view(b, 1, dd))
-        if cross:
+        if cross and nk_tot == 0:
+            dxk3 = None  # no keys, nothing flows back into the (empty) visible-token rows
+        elif cross:
             xk2 = s["xk16"].view(b * nk_tot, dd)
             if s["kv_w"] is not None:
                 dxk = engine.linear_bwd(dkv_all.view(b * nk_tot, -1), xk2, s["kv_w"])

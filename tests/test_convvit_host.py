@@ -233,3 +233,37 @@ def test_drop_scale_distribution_and_module():
     assert set(y.unique().tolist()) <= {0.0, 2.0} and (y.flatten(1).std(dim=1) == 0).all()  # whole samples dropped
     dp.eval()
     assert dp(x) is x
+
+
+_SINGLE_VIEW_GRID = [
+    ((16, 24), (16, 24), (4, 8), (2, 2), []), ((16, 24), (16, 24), (2, 4), (2, 2), [4]), ((16, 24), (16, 24), (1, 2), (2, 2), [4, 8]),
+    ((24, 32), (16, 24), (1, 2), (2, 2), [4, 8]), ((16, 24), (24, 32), (1, 2), (2, 2), [4, 8]),
+    ((16, 16, 16), (16, 16, 16), (4, 4, 4), (2, 2, 2), [4]), ((16, 16, 16), (16, 16, 16), (2, 2, 2), (2, 2, 2), [4, 8]),
+    ((16, 16, 1), (16, 16, 1), (2, 2, 1), (2, 2, 1), [4, 8]), ((32, 24, 12), (16, 16, 16), (2, 2, 2), (2, 2, 2), [4]),
+    ((32, 32, 4), (32, 32, 4), (4, 4, 1), (2, 2, 1), [4, 8]), ((32, 32, 4), (32, 32, 4), (8, 8, 1), (2, 2, 1), [4, 8]),
+    ((32, 32, 4), (32, 32, 4), (4, 4, 1), (2, 2, 1), [4, 8, 16]), ((32, 32, 4), (32, 32, 4), (2, 2, 1), (2, 2, 1), [2, 2, 4, 4]),
+]
+
+
+@pytest.mark.parametrize("input_mask", [True, False])
+@pytest.mark.parametrize("grid", range(len(_SINGLE_VIEW_GRID)))
+def test_reference_test_grid_shapes_convvit(grid, input_mask, emulated_kernels):
+    """The reference's ``TestConvViT.test_single_view`` grid (cinema/convvit_test.py:72-150): no stem / 1 - 4 stem levels,
+    anisotropic patches, inputs smaller and larger than the configured size (resampled positional table), multi-frame
+    multi-channel inputs, every reduce mode, with and without a stem mask; plus a backward pass."""
+    import math
+
+    image_size, input_size, ps, sf, chans = _SINGLE_VIEW_GRID[grid]
+    n_frames, in_chans = (3, 3) if grid % 2 else (1, 1)
+    torch.manual_seed(0)
+    vit = ConvViT(image_size_dict={"sax": image_size}, n_frames=n_frames, in_chans_dict={"sax": in_chans}, out_chans=3,
+                  enc_patch_size_dict={"sax": ps}, enc_scale_factor_dict={"sax": sf}, enc_conv_chans=chans, enc_conv_n_blocks=1,
+                  enc_embed_dim=16, enc_depth=2, enc_n_heads=2, mlp_ratio=2)
+    x = torch.rand(2, n_frames * in_chans, *input_size)
+    n_patches = math.prod(s // p for s, p in zip(input_size, vit.enc_down_dict["sax"].eff_patch_size))
+    mask_dict = {"sax": torch.rand(2, n_patches) > 0.5} if input_mask else None
+    for reduce in ("patch", "all", "cls"):
+        out = vit({"sax": x}, mask_dict=mask_dict, reduce=reduce)
+        assert out.shape == (2, 3) and bool(torch.isfinite(out).all())
+    out.sum().backward()
+    assert vit.encoder.cls_token.grad is not None and bool(torch.isfinite(vit.encoder.cls_token.grad).all())
