@@ -63,7 +63,11 @@ def test_encoder_decoder_compatibility_table(golden_dir):
     g = torch.load(golden_dir / "convunetr_2view.pt")
     for args, want in g["compat"].items():
         assert check_conv_unetr_enc_dec_compatiblity(*args) == want, args
-    # known answers of the reference's own test (cinema/segmentation/convunetr_test.py:23-63): incompatible pyramids raise
+    # the known-answer table of the reference's own test (cinema/segmentation/convunetr_test.py:23-35)
+    for args, want in [(((4, 4), (2, 2), 2, 4, (2, 2), (2, 2)), (1, 0)), (((4, 1), (2, 1), 2, 4, (2, 1), (2, 1)), (1, 0)),
+                       (((4, 4), (2, 2), 2, 5, (2, 2), (2, 2)), (1, 1)), (((2, 2), (2, 2), 2, 4, (2, 2), (2, 2)), (0, 1))]:
+        assert check_conv_unetr_enc_dec_compatiblity(*args) == want, args
+    # incompatible pyramids raise
     with pytest.raises(ValueError):
         check_conv_unetr_enc_dec_compatiblity((4, 4), (2, 2), 4, 4, (2, 2), (2, 2))  # as many conv layers as decoder levels
     with pytest.raises(ValueError):
@@ -88,3 +92,55 @@ def test_get_model_from_acdc_style_config():
     assert model.encoder.blocks[0].drop_path1.drop_prob == 0.1
     model.set_grad_ckpt(True)
     assert model.decoder_dict["sax"].grad_ckpt and model.enc_down_dict["sax"].grad_ckpt
+
+
+_UNETR_GRID = [
+    ((16, 24), (4, 8), (2, 2), [], (2, 4, 8), (1, 2), (2, 2)),
+    ((16, 24), (2, 4), (2, 2), [4], (2, 4, 8), (1, 2), (2, 2)),
+    ((16, 24), (1, 2), (2, 2), [4, 8], (2, 4, 8), (1, 2), (2, 2)),
+    ((16, 24, 16), (4, 8, 4), (2, 2, 2), [], (2, 4, 8), (1, 2, 1), (2, 2, 2)),
+    ((16, 16, 16), (4, 4, 4), (2, 2, 2), [4], (2, 4, 8, 16), (1, 1, 1), (2, 2, 2)),
+    ((16, 16, 16), (2, 2, 2), (2, 2, 2), [4, 8], (2, 4, 8, 16), (1, 1, 1), (2, 2, 2)),
+    ((16, 16, 1), (2, 2, 1), (2, 2, 1), [4, 8], (2, 4, 8, 16), (1, 1, 1), (2, 2, 1)),
+    ((32, 32, 4), (4, 4, 1), (2, 2, 1), [4, 8], (2, 4, 8, 16), (2, 2, 1), (2, 2, 1)),
+    ((32, 32, 4), (8, 8, 1), (2, 2, 1), [4, 8], (2, 4, 8, 16, 32), (2, 2, 1), (2, 2, 1)),
+    ((32, 32, 4), (4, 4, 1), (2, 2, 1), [4, 8, 16], (2, 4, 8, 16, 32), (2, 2, 1), (2, 2, 1)),
+    ((32, 32, 4), (2, 2, 1), (2, 2, 1), [2, 2, 4, 4], (2, 4, 8, 16, 32), (2, 2, 1), (2, 2, 1)),
+]
+
+
+@pytest.mark.parametrize("grid", range(len(_UNETR_GRID)))
+def test_reference_test_grid_shapes_convunetr(grid, emulated_kernels):
+    """The reference's ``TestConvUNetR.test_single_view`` grid (cinema/segmentation/convunetr_test.py:69-139): models
+    without a stem, 1 - 4 stem levels, decoders with and without extra downsampling levels, 2-D and 3-D; logits have the
+    image's shape, the grad-ckpt switch propagates, and a backward pass reaches the stem."""
+    image_size, eps, esf, chans, dec_chans, dps, dsf = _UNETR_GRID[grid]
+    in_chans, out_chans = (3, 4) if grid % 2 else (1, 2)
+    torch.manual_seed(0)
+    unetr = ConvUNetR(image_size_dict={"view": image_size}, in_chans_dict={"view": in_chans}, out_chans=out_chans,
+                      enc_patch_size_dict={"view": eps}, enc_scale_factor_dict={"view": esf}, enc_conv_chans=chans,
+                      enc_conv_n_blocks=1, enc_embed_dim=16, enc_depth=len(dec_chans), enc_n_heads=2, dec_chans=dec_chans,
+                      dec_patch_size_dict={"view": dps}, dec_scale_factor_dict={"view": dsf}, mlp_ratio=2)
+    for flag in (True, False):
+        unetr.set_grad_ckpt(flag)
+        assert all(m.grad_ckpt == flag for m in unetr.children() if hasattr(m, "grad_ckpt"))
+    x = torch.rand(2, in_chans, *image_size)
+    logits = unetr({"view": x})["view"]
+    assert logits.shape == (2, out_chans, *image_size) and bool(torch.isfinite(logits).all())
+    logits.sum().backward()
+    first = next(unetr.enc_down_dict["view"].parameters())
+    assert first.grad is not None or not first.requires_grad
+
+
+def test_reference_multi_view_convunetr(emulated_kernels):
+    """cinema/segmentation/convunetr_test.py:141-214: a 2-D and a 3-D view through one shared encoder."""
+    unetr = ConvUNetR(image_size_dict={"lax": (16, 16), "sax": (16, 24, 16)}, in_chans_dict={"lax": 1, "sax": 1}, out_chans=3,
+                      enc_patch_size_dict={"lax": (4, 8), "sax": (4, 8, 4)}, enc_scale_factor_dict={"lax": (2, 2), "sax": (2, 2, 2)},
+                      enc_conv_chans=[], enc_conv_n_blocks=1, enc_embed_dim=16, enc_depth=3, enc_n_heads=2, dec_chans=(2, 4, 8),
+                      dec_patch_size_dict={"lax": (1, 2), "sax": (1, 2, 1)}, dec_scale_factor_dict={"lax": (2, 2), "sax": (2, 2, 2)},
+                      mlp_ratio=2)
+    images = {"lax": torch.rand(2, 1, 16, 16), "sax": torch.rand(2, 1, 16, 24, 16)}
+    out = unetr(images)
+    assert out["lax"].shape == (2, 3, 16, 16) and out["sax"].shape == (2, 3, 16, 24, 16)
+    sum(v.sum() for v in out.values()).backward()
+    assert unetr.encoder.cls_token.grad is None or bool(torch.isfinite(unetr.encoder.cls_token.grad).all())
