@@ -364,8 +364,8 @@ class Attention(nn.Module):
     def forward(self, q: torch.Tensor, k: torch.Tensor | None = None) -> torch.Tensor:
         if k is not None and self.rotary is not None:
             raise ValueError("Rotary positional embedding is not supported with different query and key.")
-        if self.q.bias is None or not isinstance(self.q_norm, nn.Identity):
-            raise NotImplementedError("the B200 attention path needs qkv_bias=True and qk_norm=False (MAE configs)")
+        if not isinstance(self.q_norm, nn.Identity):
+            raise NotImplementedError("the B200 attention path needs qk_norm=False (as in every CineMA config)")
         if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
             raise NotImplementedError("attention / projection dropout is not part of the MAE hot path")
         return _AttentionFn.apply(q, k, _anchor(self), self)
