@@ -199,9 +199,12 @@ class MaskedConvBlock(nn.Module):
         self.conv1 = conv_cls(in_chans, in_chans, kernel_size=1, padding="same")
         self.conv2 = conv_cls(in_chans, in_chans, kernel_size=1, padding="same")
         self.dw_conv = conv_cls(in_chans, in_chans, kernel_size=5, padding="same", groups=in_chans)
-        if drop_path > 0.0:
-            raise NotImplementedError("drop_path in the conv stem is never enabled by the reference configs")
-        self.drop_path = nn.Identity()
+        if drop_path > 0.0:  # never enabled by the reference configs; the dense (cuDNN) form below supports it
+            from cinema_b200.vit import DropPath
+
+            self.drop_path = DropPath(drop_path)
+        else:
+            self.drop_path = nn.Identity()
         self.mlp = ConvMlp(n_dims=n_dims, in_features=in_chans, hidden_features=in_chans * mlp_ratio,
                            act_layer=act_layer, drop=dropout)
 
@@ -216,8 +219,8 @@ class MaskedConvBlock(nn.Module):
         h = self.conv1(self.norm1(x))
         if mask is not None:
             h = mask.unsqueeze(1).to(h.dtype) * h
-        x = x + self.conv2(self.dw_conv(h))
-        return x + self.mlp(self.norm2(x))
+        x = x + self.drop_path(self.conv2(self.dw_conv(h)))
+        return x + self.drop_path(self.mlp(self.norm2(x)))
 
 
 class ConvTranspose2d(nn.ConvTranspose2d):

@@ -58,6 +58,8 @@ def supported(down) -> bool:
     for stage in down.conv_blocks:
         if not isinstance(stage.patch_embed.norm, ConvLayerNorm):
             return False
+        if any(not isinstance(blk.drop_path, torch.nn.Identity) for blk in stage.conv):
+            return False
     return True
 
 
