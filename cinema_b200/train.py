@@ -33,6 +33,16 @@ def cosine_lr(step: float, warmup_steps: float, max_n_steps: float, lr: float, m
     return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * (step - warmup_steps) / (max_n_steps - warmup_steps)))
 
 
+def adjust_learning_rate(optimizer: torch.optim.Optimizer, step: float, warmup_steps: float, max_n_steps: float, lr: float,
+                         min_lr: float) -> float:
+    """Set the schedule's learning rate on a torch optimiser whose groups may carry ``lr_scale`` (layer-wise decay groups
+    of ``convvit.param_groups_lr_decay``), as the fine-tuning scripts do (cinema/optim.py:21-52).  Returns the base lr."""
+    cur = cosine_lr(step, warmup_steps, max_n_steps, lr, min_lr)
+    for group in optimizer.param_groups:
+        group["lr"] = cur * group.get("lr_scale", 1.0)
+    return cur
+
+
 def get_n_accum_steps(batch_size: int, batch_size_per_device: int, world_size: int) -> int:
     """Gradient-accumulation factor for an effective batch size (cinema/optim.py:122-143), same checks and errors."""
     per_step = batch_size_per_device * world_size

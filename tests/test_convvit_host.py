@@ -6,6 +6,8 @@ Tolerances as in test_model_host.py: the emulation rounds to bf16 where the kern
 3e-2 relative (norm-wise) on features / gradients; logits (means over tokens and views) 3e-2 of their scale.
 """
 
+import math
+
 import pytest
 import torch
 
@@ -267,3 +269,44 @@ def test_reference_test_grid_shapes_convvit(grid, input_mask, emulated_kernels):
         assert out.shape == (2, 3) and bool(torch.isfinite(out).all())
     out.sum().backward()
     assert vit.encoder.cls_token.grad is not None and bool(torch.isfinite(vit.encoder.cls_token.grad).all())
+
+
+def test_finetune_loop_with_layerwise_lr_decay(golden_dir, emulated_kernels):
+    """cinema_b200/examples/finetune.py: ConvViT + layer-wise lr-decay AdamW groups + cosine schedule with per-group
+    lr_scale fits a fixed toy batch; the lr seen by every group is schedule x its lr_scale (cinema/optim.py:47-51)."""
+    from cinema_b200.examples import finetune as ft
+    from cinema_b200.train import cosine_lr
+
+    g = torch.load(golden_dir / "convvit_2view.pt")
+    model = _model(g)
+    opt = ft.build_optimizer(model, lr=1e-3, weight_decay=0.05, layer_decay=0.75)
+    scales = sorted({grp["lr_scale"] for grp in opt.param_groups})
+    assert len(scales) == model.encoder.blocks.__len__() + 2 and abs(scales[-1] - 1.0) < 1e-12  # layers 0 .. depth + 1
+    label = torch.tensor([0, 2])
+    batches = [(g["images"], label)] * 4
+    first = ft.finetune_one_epoch(model, batches, opt, ft.classification_loss, epoch=1, n_batches=4, n_epochs=10, n_warmup_epochs=1,
+                                  lr=1e-3, min_lr=1e-6, clip_grad=1.0)
+    want = cosine_lr(1 + 3 / 4, 1, 10, 1e-3, 1e-6)
+    for grp in opt.param_groups:
+        assert abs(grp["lr"] - want * grp["lr_scale"]) < 1e-12
+    later = ft.finetune_one_epoch(model, batches, opt, ft.classification_loss, epoch=2, n_batches=4, n_epochs=10, n_warmup_epochs=1,
+                                  lr=1e-3, min_lr=1e-6, clip_grad=1.0)
+    assert later[-1] < first[0]
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_segmentation_loss_definition():
+    """Soft Dice + CE: perfect one-hot logits -> ~0, uniform logits -> (1 - 2/(1+C))-ish Dice + log C cross-entropy."""
+    from cinema_b200.examples import finetune as ft
+
+    label = torch.randint(0, 3, (2, 6, 6, 4))
+    perfect = torch.nn.functional.one_hot(label, 3).movedim(-1, 1).float() * 50.0
+    assert float(ft.segmentation_loss(perfect, label)) < 1e-3
+    uniform = torch.zeros(2, 3, 6, 6, 4)
+    dice = []
+    for b in range(2):  # per sample and class: 1 - (2 * n_c / 3) / (144 / 3 + n_c), probabilities are 1/3 everywhere
+        for c in range(3):
+            n_c = float((label[b] == c).sum())
+            dice.append(1.0 - (2.0 * n_c / 3 + 1e-5) / (144 / 3 + n_c + 1e-5))
+    want = math.log(3) + sum(dice) / len(dice)
+    assert abs(float(ft.segmentation_loss(uniform, label)) - want) < 1e-5
