@@ -35,6 +35,8 @@ _SIGNATURES = {
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "cb_conv_gemm_bf16": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p,
+                                  c_longlong, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "cb_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
     "cb_attention_fwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 4
                          + [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -185,6 +187,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None, *, a_mn: bo
                               int(accumulate), _ptr(out2), ldo2, _ptr(bias), _ptr(residual), ldr, _ptr(aux), ldaux,
                               epilogue, float(alpha), split_k, block_n, _ptr(colsum), _ptr(row_scale), int(rows_per_group),
                               _stream()), "gemm")
+
+
+def conv_gemm(x_rows: torch.Tensor, w_taps: torch.Tensor, out: torch.Tensor, row_off, *, bias: torch.Tensor | None = None,
+              residual: torch.Tensor | None = None, block_n: int = 0) -> None:
+    """EXPERIMENTAL (see include/cinema_b200.h): out[r] = sum_t x_rows[r + row_off[t]] @ w_taps[:, t*C:(t+1)*C]^T (+ bias)
+    (+ residual).  x_rows (R, C_in) bf16 zero-haloed row space, w_taps (C_out, taps * C_in) bf16, out (R, C_out) bf16 / fp32."""
+    assert x_rows.dtype == torch.bfloat16 and w_taps.dtype == torch.bfloat16
+    ldx, ldw, ldo = _row_major_2d(x_rows, "X"), _row_major_2d(w_taps, "W"), _row_major_2d(out, "out")
+    rows, c_in = x_rows.shape
+    c_out = w_taps.shape[0]
+    n_taps = len(row_off)
+    assert w_taps.shape[1] == n_taps * c_in and tuple(out.shape) == (rows, c_out)
+    out_dt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.float32 and tuple(residual.shape) == (rows, c_out)
+        ldr = _row_major_2d(residual, "residual")
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == c_out
+    _check(lib().cb_conv_gemm_bf16(_ptr(x_rows), ldx, rows, c_in, _ptr(w_taps), ldw, c_out, n_taps, _ints(row_off), _ptr(out), ldo,
+                                   out_dt, _ptr(bias), _ptr(residual), ldr, block_n, _stream()), "conv_gemm")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:

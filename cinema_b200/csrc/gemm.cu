@@ -46,6 +46,10 @@ struct GemmArgs {
   float* colsum;  // optional: column sums of the bf16 output (bias gradient of the consumer)
   const float* row_scale;  // optional: per row-group factor on (alpha * acc + bias) before the residual (stochastic depth)
   int rows_per_group;
+  // CONV instantiations only (appended: the layout seen by the GEMM instantiations is unchanged): K = taps * C_in, the A
+  // tile of k-block kb is the 2-D box of the [rows, C_in] tensor map at row m0 + conv_off[kb / conv_kb_per_tap]
+  int conv_kb_per_tap;
+  int conv_off[27];
 };
 
 // CTAS == 2: a CTA pair (cluster of two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2; each
@@ -66,7 +70,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int CTAS>
+template <int BN, bool A_MN, bool B_MN, int CTAS, bool CONV = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs p) {
   using C = Cfg<BN, CTAS>;
@@ -137,7 +141,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* sb = sa + C::A_BYTES;
           // pair: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
           if (!PAIR || cta_rank == 0) mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES * CTAS);
-          if constexpr (!A_MN) {
+          if constexpr (CONV) {
+            // implicit im2col: filter tap t reads the SAME 2-D matrix shifted by a constant number of rows; rows outside
+            // the matrix (negative or past the end) are zero-filled by TMA, which is the convolution's zero padding
+            const int tap = kb / p.conv_kb_per_tap;
+            tma_load_2d_g<CTAS>(sa, &tma_a, &full_bar[stage], (kb - tap * p.conv_kb_per_tap) * BK, m0 + p.conv_off[tap]);
+          } else if constexpr (!A_MN) {
             tma_load_2d_g<CTAS>(sa, &tma_a, &full_bar[stage], kb * BK, m0);
           } else {
 #pragma unroll
@@ -407,12 +416,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CTAS>
+template <int BN, bool A_MN, bool B_MN, int CTAS, bool CONV = false>
 int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs& p, cudaStream_t stream) {
   using C = Cfg<BN, CTAS>;
+  static_assert(!CONV || (!A_MN && !B_MN), "the convolution producer reads K-major operands");
   CUtensorMap ta, tb;
   int rc;
-  if (!A_MN)
+  if (CONV)  // the activation matrix itself: [rows, C_in]; K of the GEMM is taps * C_in
+    rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.conv_kb_per_tap * BK, (uint64_t)p.M, (uint64_t)lda * 2, BK, BM, 128);
+  else if (!A_MN)
     rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BK, BM, 128);
   else
     rc = cb_make_tmap_2d(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, BK, 128);
@@ -422,7 +434,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, GemmArgs&
   else
     rc = cb_make_tmap_2d(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, BK, 128);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CTAS>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CTAS, CONV>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -571,5 +583,47 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
     case 256: return dispatch_major<256, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
     case 128: return dispatch_major<128, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
     default: return dispatch_major<64, 1>(a_mn_major, b_mn_major, A, lda, B, ldb, p, s);
+  }
+}
+
+// EXPERIMENTAL (not on any product path yet, not validated on a GPU in round 1; see DESIGN.md section 8b and
+// tools/conv_rowspace_prototype.py for the arithmetic): 3^n "same" convolution over a zero-haloed channel-last row space
+// as one K-concatenated GEMM.  X [rows, c_in] bf16 (ldx elements per row), W [c_out, n_taps * c_in] bf16 tap-major,
+// row_off[n_taps] (host array) the constant row offset of each tap; out [rows, c_out] bf16 / fp32 (+ bias, + residual).
+extern "C" int cb_conv_gemm_bf16(const void* X, long long ldx, long long rows, int c_in, const void* W, long long ldw,
+                                 int c_out, int n_taps, const int* row_off, void* out, long long ldo, int out_dtype,
+                                 const float* bias, const float* residual, long long ldr, int block_n, void* stream) {
+  CB_CHECK_ARG(rows > 0 && rows < (1ll << 31) - 2 * BM && c_in > 0 && c_out > 0, "conv_gemm: bad problem size");
+  CB_CHECK_ARG(c_in % BK == 0, "conv_gemm: c_in=%d must be a multiple of %d (one k-block never straddles two taps)", c_in, BK);
+  CB_CHECK_ARG(c_out % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && (residual == nullptr || ldr % 4 == 0),
+               "conv_gemm: channel counts / leading dimensions must keep 16-byte row alignment");
+  CB_CHECK_ARG(n_taps >= 1 && n_taps <= 27 && row_off != nullptr, "conv_gemm: 1..27 taps");
+  CB_CHECK_ARG(out != nullptr && (out_dtype == CB_DT_BF16 || out_dtype == CB_DT_F32), "conv_gemm: bad output");
+  CB_CHECK_ARG((rows + 2 * BM) * ldo < (1ll << 31) - 1 && (rows + 2 * BM) * ldr < (1ll << 31) - 1,
+               "conv_gemm: epilogue tensors must stay below 2^31 elements");
+  GemmArgs p = {};
+  p.M = (int)rows, p.N = c_out, p.K = n_taps * c_in;
+  p.num_kb = p.K / BK;
+  p.out = out, p.ldo = ldo, p.out_fp32 = out_dtype == CB_DT_F32, p.atomic_add = 0;
+  p.bias = bias, p.residual = residual, p.ldr = ldr;
+  p.epi = CB_EPI_NONE, p.alpha = 1.0f, p.rows_per_group = 1;
+  p.conv_kb_per_tap = c_in / BK;
+  for (int t = 0; t < n_taps; ++t) p.conv_off[t] = row_off[t];
+  int bn = block_n;
+  if (bn != 64 && bn != 128 && bn != 256) bn = c_out > 128 ? 256 : (c_out > 64 ? 128 : 64);
+  const long long pair_tiles = (rows + 2 * BM - 1) / (2 * BM) * ((c_out + bn - 1) / bn);
+  const int ctas = (bn > 64 && pair_tiles >= cb_sm_count() / 2) ? 2 : 1;  // pairs once every pair slot has a tile
+  p.num_m_tiles = (int)((rows + (long long)BM * ctas - 1) / (BM * ctas));
+  p.num_n_tiles = (c_out + bn - 1) / bn;
+  p.splits = 1, p.kb_per_split = p.num_kb;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ctas == 2) {
+    if (bn == 256) return launch<256, false, false, 2, true>(X, ldx, W, ldw, p, s);
+    return launch<128, false, false, 2, true>(X, ldx, W, ldw, p, s);
+  }
+  switch (bn) {
+    case 256: return launch<256, false, false, 1, true>(X, ldx, W, ldw, p, s);
+    case 128: return launch<128, false, false, 1, true>(X, ldx, W, ldw, p, s);
+    default: return launch<64, false, false, 1, true>(X, ldx, W, ldw, p, s);
   }
 }

@@ -56,6 +56,18 @@ int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, lo
                  int epilogue, float alpha, int split_k, int block_n, float* colsum, const float* row_scale,
                  int rows_per_group, void* stream);
 
+/* EXPERIMENTAL -- exported for the next round's segmentation decoder, not used by any product path yet and not validated
+ * on a GPU in round 1 (arithmetic pinned on the CPU: tools/conv_rowspace_prototype.py, tests/test_conv_rowspace_design.py).
+ * 3^n "same" convolution over a zero-haloed channel-last ROW SPACE as one K-concatenated tcgen05 GEMM:
+ *   out[r, :] = sum_t X[r + row_off[t], :] . W[:, t*c_in : (t+1)*c_in]^T (+ bias) (+ residual),  rows outside [0, rows) read 0.
+ * X [rows, c_in] bf16 (c_in % 64 == 0), W [c_out, n_taps*c_in] bf16 tap-major, row_off: HOST array of n_taps <= 27 ints.
+ * Replaces nn.Conv3d / nn.Conv2d with kernel 3, padding "same" of ConvResBlock (cinema/conv.py:314-315) in the UNETR decoder
+ * (cinema/segmentation/convunetr.py:66-81,340-388); the same entry point computes the input gradient (negated offsets,
+ * transposed weights). */
+int cb_conv_gemm_bf16(const void* X, long long ldx, long long rows, int c_in, const void* W, long long ldw, int c_out,
+                      int n_taps, const int* row_off, void* out, long long ldo, int out_dtype, const float* bias,
+                      const float* residual, long long ldr, int block_n, void* stream);
+
 /* column sums of a bf16 [M,N] matrix accumulated (atomically) into fp32 out[N]: bias gradients.
  * Replaces the reduce kernels autograd runs for nn.Linear bias (same call sites as above). */
 int cb_colsum_bf16(const void* X, long long ldx, int M, int N, float* out, void* stream);

@@ -61,6 +61,25 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, accumulate=False, out2=None, bias
         out2.copy_(acc.to(BF16))
 
 
+def conv_gemm(x_rows, w_taps, out, row_off, *, bias=None, residual=None, block_n=0):
+    """out[r] = sum_t x_rows[r + off_t] @ W_t^T: rows outside the matrix read as zero (what the TMA producer delivers)."""
+    r, c_in = x_rows.shape
+    x = x_rows.float()
+    acc = torch.zeros((r, w_taps.shape[0]), dtype=torch.float64)
+    for t, off in enumerate(row_off):
+        sh = torch.zeros_like(x)
+        lo, hi = max(0, -off), min(r, r - off)
+        if hi > lo:
+            sh[lo:hi] = x[lo + off:hi + off]
+        acc += sh.double() @ w_taps[:, t * c_in:(t + 1) * c_in].double().t()
+    acc = acc.float()
+    if bias is not None:
+        acc = acc + bias.float()
+    if residual is not None:
+        acc = acc + residual
+    out.copy_(acc.to(out.dtype))
+
+
 def colsum(x, out):
     out.add_(x.float().sum(0))
 
@@ -390,6 +409,7 @@ def device_info():
 
 
 ALL = [
+    "conv_gemm",
     "gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16", "mask_to_index",
     "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize", "patchify",
     "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply", "sumsq", "adamw_flat", "expand_token_index", "dwconv_tokens", "dwconv_tokens_wgrad",
