@@ -323,3 +323,29 @@ def test_reference_test_grid_shapes_mae(grid, enc_mask_ratio, cross_attn, emulat
     if torch.isfinite(loss):
         loss.backward()
         assert all(torch.isfinite(p.grad).all() for p in mae.parameters() if p.grad is not None)
+
+
+def test_mae_reconstruction_example(golden_dir, emulated_kernels):
+    """cinema_b200/examples/inference.py (cinema/examples/inference/mae.py:57-83): visible patches keep the input voxels bit
+    for bit, masked patches hold the model's predictions, the mask image marks exactly the masked patches."""
+    from cinema_b200.examples.inference import mae_reconstruct, reconstruct_images
+
+    g = torch.load(golden_dir / "mae_small_4view.pt")
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    torch.manual_seed(0)
+    loss, recon, masks = mae_reconstruct(model, g["images"], 0.75)
+    assert torch.isfinite(loss) and set(recon) == set(g["images"])
+    for v, img in g["images"].items():
+        assert recon[v].shape == img.shape and masks[v].shape == img.shape
+        vis = masks[v] == 0
+        assert torch.equal(recon[v][vis], img[vis])
+        frac = float(masks[v].mean())
+        n = model.enc_down_dict[v].patch_embed.n_patches
+        assert abs(frac - (n - int(n * 0.25)) / n) < 1e-6
+    # with the golden predictions / masks the pasted patches are exactly the reference's predictions
+    grids = {v: model.enc_down_dict[v].patch_embed.grid_size for v in g["preds"]}
+    recon, masks = reconstruct_images(g["images"], g["preds"], g["masks"], model.dec_patch_size_dict, grids)
+    for v in g["preds"]:
+        back = bvit.patchify(recon[v], model.dec_patch_size_dict[v])
+        assert torch.equal(back[g["masks"][v]], g["preds"][v].reshape(-1, g["preds"][v].shape[-1]))
