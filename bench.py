@@ -14,8 +14,11 @@ One JSON line is printed by rank 0:
              every step's loss inside the timed region
   roofline   the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, measured live in an
              instrumented step, against the measured bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline  the oracle (CPU port of the reference path, fp32, torch threads = host cores) on a bounded sample
-``--impl reference`` times that CPU path alone (the reference is pure Python + torch).
+  cpu_baseline  the reference's own CPU path (unmodified reference modules from baseline/_ref, fp32, torch threads = host
+             cores; the oracle port when that install did not travel) on a bounded sample
+  stock_gpu_baseline  the unmodified reference modules on the SAME GPU in the same process (bf16 autocast + SDPA +
+             GradScaler / clip / AdamW, the reference's loop; grad_ckpt on and off; DDP when N > 1): the number to beat
+``--impl reference`` times the CPU path alone (the reference is pure Python + torch).
 """
 
 from __future__ import annotations
@@ -143,6 +146,12 @@ class ClockSampler:
 # CPU arm: the oracle (port of the reference path) on the host cores
 # ------------------------------------------------------------------------------------------
 def cpu_reference_throughput(kw: dict, sample_b: int, steps: int, warmup: int) -> dict:
+    """The reference's own CPU path: the unmodified reference modules from ``baseline/_ref`` when the install travelled
+    with the repo (``kind: reference``), else the oracle port (``kind: port``)."""
+    from baseline import stock
+
+    if stock.available():
+        return stock.cpu_step_time(kw, synthetic_batch(kw, sample_b, seed=0, pin=False), steps, warmup)
     from oracle import cinema_oracle as oracle
 
     cores = os.cpu_count() or 1
@@ -302,6 +311,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the timed host-buffer pass")
+    ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock torch arm (unmodified reference on the same GPU)")
+    ap.add_argument("--stock-steps", type=int, default=5)
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -439,6 +450,31 @@ def main() -> None:
                                               "note": "tcgen05 flash attention (head_dim 64 encoder / 32 decoder); "
                                                       "4 BHNqNkd fwd, 8 BHNqNkd bwd credited"}
         line["kernel_profile"] = prof
+    if not args.no_stock_gpu:
+        # the number to beat (north_star): the UNMODIFIED reference modules on this same GPU, same batch, same process,
+        # after our own timing is finished; all ranks take part when N > 1 (DistributedDataParallel, cinema/device.py:86-104)
+        from baseline import stock
+
+        if stock.available():
+            del trainer, model
+            torch.cuda.empty_cache()
+            arms = []
+            for ckpt in (True, False):  # reference default (cinema/mae/config.yaml:3) first, then the faster setting
+                r = stock.stock_gpu_step_time(kw, host, dev, steps=args.stock_steps, warmup=3, grad_ckpt=ckpt,
+                                              ddp=world > 1, local_rank=local_rank)
+                t = torch.tensor([r["ms_per_step"]], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r["ms_per_step"] = round(float(t), 3)
+                r["value"] = round(args.batch * world / (float(t) / 1e3), 2)
+                arms.append(r)
+            best = max(arms, key=lambda r: r["value"])
+            line["stock_gpu_baseline"] = {**best, "n_gpus": world, "arms": [
+                {k: a[k] for k in ("grad_ckpt", "value", "ms_per_step", "peak_mem_gib")} for a in arms],
+                "speedup_e2e": round(e2e_value / best["value"], 2) if e2e_value == e2e_value else None,
+                "speedup_vs_reference_default_grad_ckpt": round(e2e_value / arms[0]["value"], 2) if e2e_value == e2e_value else None}
+        else:
+            line["stock_gpu_baseline"] = {"unavailable": "baseline/_ref not installed (python baseline/install_reference.py)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(kw, 2, 2, 1)
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

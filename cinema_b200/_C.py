@@ -107,6 +107,8 @@ def _check(rc: int, what: str) -> None:
 
 
 def _stream() -> int:
+    """Stream of the CURRENT device.  The library keeps per-process state for the current device (SM count, opt-in
+    shared-memory attributes), so kernels must be launched with the tensors' device current: `_ptr` checks that."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -115,6 +117,9 @@ def _ptr(t: torch.Tensor | None) -> int | None:
         return None
     if not t.is_cuda:
         raise RuntimeError("cinema_b200 kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"cinema_b200 launches on the current device (cuda:{torch.cuda.current_device()}) but got a tensor on "
+                           f"{t.device}: call torch.cuda.set_device({t.device.index}) first (one process per GPU)")
     return t.data_ptr()
 
 

@@ -638,6 +638,17 @@ class _DirectCtx:
 # ------------------------------------------------------------------------------------------
 # the module
 # ------------------------------------------------------------------------------------------
+def _uniform_mask_count(m: torch.Tensor, view: str) -> int:
+    """Number of removed patches per sample of a user-supplied mask.  Every sample must remove the same number: the
+    reference's ``x[~mask].reshape(batch, n_keep, -1)`` (cinema/mae/mae.py:550) raises otherwise, and so does this (one
+    host read; masks drawn by ``forward`` itself have static counts and never come through here)."""
+    counts = m.sum(1)
+    n = int(counts[0])
+    if not bool((counts == n).all()):
+        raise ValueError(f"enc_mask_dict[{view!r}] removes a different number of patches per sample: {counts.tolist()}")
+    return n
+
+
 class CineMA(nn.Module):
     """Cine masked autoencoder (cinema/mae/mae.py:285-642) -- same constructor, attributes and state dict."""
 
@@ -772,7 +783,7 @@ class CineMA(nn.Module):
             n_patches = math.prod(grid)
             if enc_mask_dict is not None:
                 m = enc_mask_dict[v].to(device=dev, dtype=torch.bool)
-                n_keeps.append(n_patches - int(m[0].sum()))
+                n_keeps.append(n_patches - _uniform_mask_count(m, v))
             else:
                 m = get_batch_random_patch_mask(b, n_patches, enc_mask_ratio, dev)
                 n_keeps.append(n_patches if enc_mask_ratio == 0 else int(n_patches * (1 - enc_mask_ratio)))
@@ -819,7 +830,7 @@ class CineMA(nn.Module):
             n_patches = math.prod(grid)
             if enc_mask_dict is not None:  # given masks (tests / comparisons), as in forward()
                 masks.append(enc_mask_dict[v].to(device=dev, dtype=torch.bool))
-                n_keeps.append(n_patches - int(masks[-1][0].sum()))
+                n_keeps.append(n_patches - _uniform_mask_count(masks[-1], v))
             else:
                 masks.append(get_batch_random_patch_mask(b, n_patches, enc_mask_ratio, dev))
                 n_keeps.append(n_patches if enc_mask_ratio == 0 else int(n_patches * (1 - enc_mask_ratio)))

@@ -53,6 +53,27 @@ def get_n_accum_steps(batch_size: int, batch_size_per_device: int, world_size: i
     return batch_size // per_step
 
 
+def allreduce_gradients(model: nn.Module, process_group=None, average: bool = True) -> None:
+    """Data-parallel gradient exchange for the EAGER loops (fine-tuning ``ConvViT`` / ``ConvUNetR``, eager ``CineMA``):
+    the replacement for wrapping the model in ``DistributedDataParallel`` (cinema/device.py:86-104).
+
+    The fused autograd nodes of this package write parameter gradients straight into the flat gradient arena (every
+    ``p.grad`` is a view of it), so ``AccumulateGrad`` hooks never fire for the backbone and DDP's reducer would never
+    see those gradients: **do not wrap these models in DDP**.  Call this after ``loss.backward()`` and before
+    ``optimizer.step()`` instead -- ONE sum all-reduce over the whole arena (heads included), divided by the world size
+    like DDP's mean.  With gradient accumulation call it on the last micro-step only.  No-op on one rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(process_group)
+    if world == 1:
+        return
+    arena = ensure_arena(model)
+    arena.prepare_grads()
+    dist.all_reduce(arena.gflat, op=dist.ReduceOp.SUM, group=process_group)
+    if average:
+        arena.gflat.div_(world)
+
+
 class FlatAdamW:
     """AdamW over the flat arena with global-norm clipping (cinema/mae/pretrain.py:365-367, cinema/optim.py:204-212)."""
 
@@ -66,19 +87,35 @@ class FlatAdamW:
         self.v = torch.zeros_like(arena.flat32)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(4, dtype=torch.float32)
+        # step() never synchronises with the host, which may therefore run several steps ahead of the device: every
+        # step's scalars get their own pinned slot, and a slot is rewritten only after the async copy that read it has
+        # completed (CUDA event per slot), so an in-flight H2D copy can never pick up a later step's values
+        self._hyper_ring = [torch.zeros(4, dtype=torch.float32) for _ in range(self.HYPER_SLOTS)]
+        self._hyper_done: list = [None] * self.HYPER_SLOTS
         if dev.type == "cuda":
-            self._hyper_host = self._hyper_host.pin_memory()
+            self._hyper_ring = [t.pin_memory() for t in self._hyper_ring]
         self.t = 0
         self.segments = [s for s in arena.segments() if s[2] != 2]
 
+    HYPER_SLOTS = 8
+
     def set_step_scalars(self) -> None:
-        """Host -> device copy of {lr, 1 - beta1^t, 1 - beta2^t} for the NEXT ``apply`` (outside any CUDA graph)."""
+        """Host -> device copy of {lr, 1 - beta1^t, 1 - beta2^t} for the NEXT ``apply`` (outside any CUDA graph).
+        Note: ``t`` counts updates issued by the host; a step the device skips for a non-finite gradient norm
+        (GradScaler semantics, csrc/optim.cu) still advances the bias corrections, unlike torch's GradScaler + AdamW."""
         self.t += 1
-        self._hyper_host[0] = self.lr
-        self._hyper_host[1] = 1.0 - self.betas[0] ** self.t
-        self._hyper_host[2] = 1.0 - self.betas[1] ** self.t
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        slot = self.t % self.HYPER_SLOTS
+        if self._hyper_done[slot] is not None:
+            self._hyper_done[slot].synchronize()  # the copy issued HYPER_SLOTS steps ago has read this slot
+        host = self._hyper_ring[slot]
+        host[0] = self.lr
+        host[1] = 1.0 - self.betas[0] ** self.t
+        host[2] = 1.0 - self.betas[1] ** self.t
+        self.hyper.copy_(host, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.hyper.device))
+            self._hyper_done[slot] = ev
 
     def apply(self, grad_scale: float = 1.0) -> None:
         """Norm + clip + AdamW + bf16 shadow refresh; graph-capturable (no host-dependent values)."""

@@ -203,3 +203,43 @@ def test_get_n_accum_steps_and_cosine_lr():
     assert abs(cosine_lr(10, 10, 100, 1e-3, 1e-5) - 1e-3) < 1e-12
     assert abs(cosine_lr(55, 10, 100, 1e-3, 1e-5) - (1e-5 + (1e-3 - 1e-5) * 0.5 * (1 + math.cos(math.pi * 0.5)))) < 1e-12
     assert abs(cosine_lr(100, 10, 100, 1e-3, 1e-5) - 1e-5) < 1e-12
+
+
+def _helper_worker(rank, world, port, out):
+    _patch()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from cinema_b200 import CineMA
+    from cinema_b200.train import allreduce_gradients
+
+    g = torch.load(GOLDEN)
+    model = CineMA(**g["kw"])
+    model.load_state_dict(g["state_dict"])
+    model.train()
+    images = {k: v[rank:rank + 1] for k, v in g["images"].items()}
+    masks = {k: v[rank:rank + 1] for k, v in g["masks"].items()}
+    loss, _, _, _ = model(images, g["ratio"], enc_mask_dict=masks)
+    loss.backward()
+    local = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    allreduce_gradients(model)
+    mean = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    if rank == 0:
+        want = {k: (gathered[0][k] + gathered[1][k]) / 2 for k in local}
+        worst = max(float((mean[k] - want[k]).abs().max()) for k in want)
+        torch.save({"worst": worst, "n": len(want)}, out)
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_helper(tmp_path):
+    """Eager data-parallel loops: ``allreduce_gradients`` after ``backward`` leaves every ``p.grad`` equal to
+    the mean of the ranks' local gradients -- DDP's semantics without the DDP wrapper."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "h.pt"
+    mp.spawn(_helper_worker, args=(2, port, str(out)), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["n"] > 100 and res["worst"] < 1e-6, res

@@ -31,6 +31,8 @@ def bf16_randn(*shape, scale=1.0, seed=0):
 GEMM_SHAPES = [
     (128, 256, 64), (128, 128, 128), (256, 512, 768), (1154, 768, 768), (1154, 3072, 768), (1154, 768, 3072),
     (300, 256, 512), (77, 64, 16), (50, 16, 16), (129, 24, 40), (2305, 512, 2048), (513, 1536, 768),
+    # ViT-L (cinema/vit.py:807-822: dim 1024, mlp 4096, qkv 3072) at two-sample token counts (2 x 769 rows)
+    (1538, 1024, 1024), (1538, 4096, 1024), (1538, 1024, 4096), (1538, 3072, 1024), (1538, 512, 1024),
 ]
 
 
@@ -47,7 +49,8 @@ def test_gemm_forward_kmajor(m, n, k, block_n):
     assert rel_err(out16, ref) < 3e-3  # one bf16 rounding of the output (2^-9 relative per element)
 
 
-@pytest.mark.parametrize("m,n,k", [(1154, 768, 3072), (1154, 3072, 768), (300, 512, 256), (77, 16, 64), (2305, 512, 512)])
+@pytest.mark.parametrize("m,n,k", [(1154, 768, 3072), (1154, 3072, 768), (300, 512, 256), (77, 16, 64), (2305, 512, 512),
+                                   (1538, 1024, 4096), (1538, 4096, 1024), (1538, 1024, 3072)])
 def test_gemm_dgrad_b_mn_major(m, n, k):
     # dX[m, n] = dY[m, k] @ W[k, n]  with W stored (k rows, n contiguous) == B MN-major
     dy, w = bf16_randn(m, k, seed=3), bf16_randn(k, n, scale=0.05, seed=4)
@@ -57,7 +60,8 @@ def test_gemm_dgrad_b_mn_major(m, n, k):
 
 
 @pytest.mark.parametrize("t,n,k", [(1154, 768, 768), (1154, 3072, 768), (1154, 768, 3072), (9232, 768, 768),
-                                   (300, 256, 512), (77, 16, 64), (130, 64, 16), (4610, 512, 2048)])
+                                   (300, 256, 512), (77, 16, 64), (130, 64, 16), (4610, 512, 2048),
+                                   (1538, 1024, 4096), (1538, 4096, 1024), (12304, 3072, 1024)])
 @pytest.mark.parametrize("split_k", [0, 1, 3])
 def test_gemm_wgrad_both_mn_major_accumulate(t, n, k, split_k):
     # dW[n, k] += dY[t, n]^T @ X[t, k]
@@ -77,7 +81,7 @@ def test_gemm_a_mn_b_k():
     assert rel_err(out, a.float().t() @ b.float().t()) < 2e-5
 
 
-@pytest.mark.parametrize("m,n,k", [(1154, 3072, 768), (130, 64, 16), (2305, 2048, 512)])
+@pytest.mark.parametrize("m,n,k", [(1154, 3072, 768), (130, 64, 16), (2305, 2048, 512), (1538, 4096, 1024)])
 def test_gemm_bias_gelu_epilogue(m, n, k):
     a, b = bf16_randn(m, k, seed=9), bf16_randn(n, k, scale=0.05, seed=10)
     bias = torch.randn(n, device=DEV) * 0.1
