@@ -669,8 +669,11 @@ def test_trainer_steps_without_host_sync_match_synced_steps(golden_dir):
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
         out[sync] = ([float(x) for x in losses], tr.arena.flat32.clone())
-    assert all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(out[False][0], out[True][0])), (out[False][0], out[True][0])
-    assert rel(out[False][1], out[True][1]) < 1e-3  # fp32 atomics reorder sums; a wrong bias correction would be ~1e-1
+    # fp32 atomics reorder sums and twelve updates at lr 2e-3 amplify that; one wrong bias correction (e.g. step 1 using
+    # step 2's: update x 0.53) moves the parameters by ~1e-2 and the following losses by > 1e-2
+    worst = max(abs(a - b) / abs(b) for a, b in zip(out[False][0], out[True][0]))
+    assert worst <= 2e-3, (worst, out[False][0], out[True][0])
+    assert rel(out[False][1], out[True][1]) < 5e-3
 
 
 def test_user_masks_with_ragged_counts_are_rejected(golden_dir):
