@@ -32,6 +32,7 @@ _SIGNATURES = {
     "cb_last_error": (c_char_p, []),
     "cb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cb_set_pdl": (c_int, [c_int]),
+    "cb_attention_trace": (c_int, [c_void_p]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),

@@ -17,7 +17,25 @@
 #include "../../include/cinema_b200.h"
 #include "common.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
+// In-kernel clock trace (diagnostics, cb_attention_trace): when a device buffer is registered, ONE CTA in the middle of
+// the grid stamps clock64() at the phase boundaries of one softmax / compute warp per role and of its MMA warp
+// (slot layout: tools/attn_trace.py).  A null pointer (the default) costs one predicated-off store per stamp.
+__device__ long long* g_attn_trace = nullptr;
+
+extern "C" int cb_attention_trace(long long* device_buf) {
+  CB_CUDA(cudaMemcpyToSymbol(g_attn_trace, &device_buf, sizeof(device_buf)));
+  return 0;
+}
+
 namespace {
+
+#define CB_TR(slot)                                  \
+  do {                                               \
+    if (tron) trace[(slot)] = clock64();             \
+  } while (0)
 
 constexpr int TQ = 128;       // query rows per tile (UMMA M)
 constexpr int TK = 128;       // keys per tile (UMMA N of S, K extent of P.V)
@@ -315,6 +333,349 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward, second generation (default): ONE 128-query tile per CTA, 256 threads, TWO CTAs per SM.
+//   warps 0-3 : softmax warpgroup (thread == query row == TMEM lane)          216 registers (setmaxnreg)
+//   warp 4    : TMA producer (Q once, K_j / V_j double buffered)              40 registers
+//   warp 5    : MMA issuer (S = Q K_j^T, O += P V_j with P as the TMEM A operand)
+//   warps 6-7 : idle (they only make the light warpgroup complete for setmaxnreg)
+// TMEM per CTA: S (128 columns) | P (64, packed bf16) | O (head_dim)  = 256 columns, so two CTAs share the SM's 512.
+// Why: the first-generation kernel (two query tiles ping-ponging inside one 384-thread CTA) spends ~7 k clocks per CTA in
+// launch / TMEM allocation / first loads / epilogue and runs its two softmax warpgroups in lock step, so the MUFU pipe
+// idles during every row-max / TMEM-load phase (profiles/r01_attention_clock_trace.md: 3.5 k clocks per key tile against
+// a 2.0 k MUFU bound).  Two independent CTAs per SM desynchronise by themselves: one CTA's exp2 phase runs under the
+// other's prologue, row max, rescale or epilogue, and the hardware block scheduler balances ragged tiles.
+// Ragged shapes cost what they contain: the last key tile is evaluated over ceil(valid / 32) * 32 columns only (S MMA
+// with a narrower N, fewer exponentials, fewer P.V k-steps), and warps whose 32 query rows are all past Nq skip the
+// softmax arithmetic (they still take part in the barrier protocol).
+// ---------------------------------------------------------------------------------------------
+constexpr int FWD2_THREADS = 256;
+
+template <int D>
+struct Fwd2Cfg {
+  static constexpr int ROW_BYTES = D * 2;
+  static constexpr uint64_t SWZ = D == 64 ? UMMA_SW128 : UMMA_SW64;
+  static constexpr int GROUP_BYTES = 8 * ROW_BYTES;
+  static constexpr int TILE_BYTES = TQ * ROW_BYTES;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
+  static constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
+  static constexpr int OFF_BAR = OFF_V + 2 * TILE_BYTES;
+  static constexpr int SMEM_USED = OFF_BAR + 256 + 1024;
+  // at least 80 KB are requested so that never more than two CTAs are resident per SM: a third one would hold
+  // registers while it waits for TMEM columns, and the setmaxnreg.inc of the first two could starve
+  static constexpr int SMEM_BYTES = SMEM_USED > 80 * 1024 ? SMEM_USED : 80 * 1024;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int TMEM_S = 0, TMEM_P = 128, TMEM_O = 192;
+  static_assert(TMEM_O + D <= TMEM_COLS, "TMEM budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(FWD2_THREADS, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdArgs p) {
+  using C = Fwd2Cfg<D>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;  // 4 warp arrivals
+  uint64_t* p_full = bars + 11;  // 4 warp arrivals
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q0 = blockIdx.x * TQ;
+  const int n_kv = (p.Nk + TK - 1) / TK;
+  const int last_nc = (p.Nk - (n_kv - 1) * TK + 31) >> 5;  // 32-column chunks of the last key tile that hold keys (1..4)
+  long long* const trace = g_attn_trace;
+  const bool tron = trace != nullptr && lane == 0 && blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == gridDim.z / 2;
+  if (warp == 0) CB_TR(240);
+
+  if (warp == 5) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1), mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1), mbar_init(&v_empty[i], 1);
+      }
+      mbar_init(s_full, 1), mbar_init(s_free, 4), mbar_init(p_full, 4), mbar_init(pv_done, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: setup done, wait for the kernels that produce Q / K / V before the first load
+  if (warp == 0) CB_TR(241);
+
+  if (warp >= 4) {
+    // 2 CTAs x (4 x 32 x 216 + 4 x 32 x 40) registers == 64 K: the light warpgroup hands its share to the softmax warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 4) {
+      // ------------------------------------------------ TMA producer
+      if (lane == 0) {
+        mbar_expect_tx(q_full, C::TILE_BYTES);
+        tma_load_4d(smem + C::OFF_Q, &tm_q, q_full, 0, h, q0, b);
+        for (int j = 0; j < n_kv; ++j) {
+          const int s = j & 1;
+          const uint32_t ph = (j >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_expect_tx(&k_full[s], C::TILE_BYTES);
+          tma_load_4d(smem + C::OFF_K + s * C::TILE_BYTES, &tm_k, &k_full[s], 0, h, j * TK, b);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_expect_tx(&v_full[s], C::TILE_BYTES);
+          tma_load_4d(smem + C::OFF_V + s * C::TILE_BYTES, &tm_v, &v_full[s], 0, h, j * TK, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 5) {
+      // ------------------------------------------------ MMA issuer
+      // The WHOLE warp runs this loop converged (every lane waits on the barriers) and one elected lane issues: under
+      // `if (lane == 0)` nvcc wraps every tcgen05 instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and
+      // rebuilds its descriptors in front of it (~67 clocks per MMA, ~100 per commit measured with the clock trace);
+      // with the elect.sync predicate the UTCHMMA / UTCBAR instructions are issued back to back from hoisted operands.
+      const bool leader = elect_one_sync() != 0;
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, D, false, true);
+      const uint32_t q_base = smem_u32(smem + C::OFF_Q);
+      const uint32_t k_base = smem_u32(smem + C::OFF_K);
+      const uint32_t v_base = smem_u32(smem + C::OFF_V);
+      auto issue_s = [&](int j) {
+        const uint32_t idesc_s = umma_idesc_bf16(TQ, j == n_kv - 1 ? last_nc * 32 : TK, false, false);
+        const uint32_t ks = k_base + (j & 1) * C::TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = umma_smem_desc(q_base + kk * 32, 0, C::GROUP_BYTES, C::SWZ);
+          const uint64_t db = umma_smem_desc(ks + kk * 32, 0, C::GROUP_BYTES, C::SWZ);
+          umma_bf16_ss(tmem_base + C::TMEM_S, da, db, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tcgen05_fence_after();
+      if (leader) issue_s(0);
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_free, j & 1);  // the softmax warps hold S(j) in registers
+          if (j < 8) CB_TR(16 * j + 8);
+          tcgen05_fence_after();
+          if (leader) {
+            issue_s(j + 1);
+            umma_commit(&k_empty[j & 1]);  // (covers S(j+1) too: that only delays the refill of the OTHER stage's successor)
+          }
+          __syncwarp();
+          if (j < 8) CB_TR(16 * j + 9);
+        }
+        mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
+        if (j < 8) CB_TR(16 * j + 10);
+        tcgen05_fence_after();
+        if (leader) {
+          const uint32_t vs = v_base + (j & 1) * C::TILE_BYTES;
+          const int n_kk = j == n_kv - 1 ? last_nc * 2 : TK / 16;  // 16 keys per step; the ragged tile stops early
+#pragma unroll
+          for (int kk = 0; kk < TK / 16; ++kk) {
+            if (kk < n_kk) {
+              const uint64_t db = umma_smem_desc(vs + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+              umma_bf16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_P + kk * 8, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(pv_done);
+          umma_commit(&v_empty[j & 1]);
+        }
+        __syncwarp();
+        if (j < 8) CB_TR(16 * j + 11);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax warpgroup
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int r = warp * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool warp_live = q0 + warp * 32 < p.Nq;  // warp-uniform: do any of this warp's 32 rows exist?
+    float m_ref = -INFINITY;  // reference max (log2 domain) the accumulators are expressed against
+    float l = 0.f;
+    const float sc = p.scale_log2;
+
+    // one key tile of NC * 32 columns
+    auto tile = [&](auto nc_c, const int j) {
+      constexpr int NC = decltype(nc_c)::value;
+      constexpr int W = NC * 32;
+      const bool trj = warp == 0 && j < 8;
+      if (trj) CB_TR(16 * j + 0);
+      mbar_wait(s_full, j & 1);
+      if (trj) CB_TR(16 * j + 1);
+      tcgen05_fence_after();
+      float s[W];  // raw scores; scale and running max are folded into the exp2 argument below
+      if (warp_live) {
+        uint32_t v[NC][32];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_32x32b_x32(lane_addr + C::TMEM_S + c * 32, v[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[c][i]);
+      }
+      if (trj) CB_TR(16 * j + 2);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+
+      float alpha = 1.0f;
+      bool grow = false;
+      if (warp_live) {
+        const int valid = p.Nk - j * TK;  // keys of this tile that exist
+        if (valid < W) {                  // ragged last tile only (CTA-uniform); kept out of line on purpose
+          asm volatile("" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < W; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+          asm volatile("" ::: "memory");
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < W; i += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], fmaxf(s[i + 2 * u], s[i + 2 * u + 1]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;  // scale > 0
+        // lazy rescale: keep m_ref unless the row max ran away by more than 2^8
+        grow = mx > m_ref + RESCALE_THRESHOLD;
+        const float m_new = grow ? mx : m_ref;
+        alpha = grow ? ex2_approx(m_ref - m_new) : 1.0f;  // 2^(-inf) = 0 on the first tile
+        m_ref = m_new;
+      }
+      if (trj) CB_TR(16 * j + 3);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // P and O are quiescent
+        if (trj) CB_TR(16 * j + 4);
+        tcgen05_fence_after();
+        if (warp_live && __any_sync(0xffffffffu, grow)) {
+#pragma unroll
+          for (int c = 0; c < D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(lane_addr + C::TMEM_O + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(lane_addr + C::TMEM_O + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      if (warp_live) {
+        l *= alpha;
+        const float neg_m = -m_ref;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int blk = 0; blk < NC; ++blk) {  // 32 keys -> 16 packed columns of this row's P in TMEM
+          uint32_t pw[16];
+#pragma unroll
+          for (int w = 0; w < 16; w += 2) {
+            const int i0 = blk * 32 + w * 2;
+            const float e0 = ex2_approx(fmaf(s[i0], sc, neg_m)), e1 = ex2_approx(fmaf(s[i0 + 1], sc, neg_m));
+            const float e2 = ex2_approx(fmaf(s[i0 + 2], sc, neg_m)), e3 = ex2_approx(fmaf(s[i0 + 3], sc, neg_m));
+            sum4[0] += e0, sum4[1] += e1, sum4[2] += e2, sum4[3] += e3;
+            pw[w] = pack_bf16(e0, e1), pw[w + 1] = pack_bf16(e2, e3);
+          }
+          tmem_st_32x32b_x16(lane_addr + C::TMEM_P + blk * 16, pw);
+        }
+        tmem_st_wait();
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      }
+      if (trj) CB_TR(16 * j + 5);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    };
+
+    for (int j = 0; j + 1 < n_kv; ++j) tile(std::integral_constant<int, 4>{}, j);
+    switch (last_nc) {
+      case 1: tile(std::integral_constant<int, 1>{}, n_kv - 1); break;
+      case 2: tile(std::integral_constant<int, 2>{}, n_kv - 1); break;
+      case 3: tile(std::integral_constant<int, 3>{}, n_kv - 1); break;
+      default: tile(std::integral_constant<int, 4>{}, n_kv - 1); break;
+    }
+
+    // epilogue: O / l -> bf16, LSE
+    if (warp == 0) CB_TR(242);
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    if (warp == 0) CB_TR(243);
+    tcgen05_fence_after();
+    const int q_row = q0 + r;
+    if (warp_live) {
+      const float inv_l = 1.0f / l;
+      bf16* o_ptr = p.o + (long long)b * p.o_sb + (long long)q_row * p.o_sn + (long long)h * p.o_sh;
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(lane_addr + C::TMEM_O + c * 16, o);
+        tmem_ld_wait();
+        if (q_row < p.Nq) {
+          uint4 w0 = make_uint4(pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l),
+                                pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l),
+                                pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l),
+                                pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l));
+          uint4 w1 = make_uint4(pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l),
+                                pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l),
+                                pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l),
+                                pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l));
+          reinterpret_cast<uint4*>(o_ptr + c * 16)[0] = w0;
+          reinterpret_cast<uint4*>(o_ptr + c * 16)[1] = w1;
+        }
+      }
+      if (q_row < p.Nq)
+        p.lse[((long long)b * p.H + h) * p.Nq + q_row] = (m_ref + log2f(l)) * (1.0f / LOG2E);
+    }
+    if (warp == 0) CB_TR(244);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+  if (warp == 0) CB_TR(245);
+}
+
+template <int D>
+int launch_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdArgs& a,
+                cudaStream_t stream) {
+  using C = Fwd2Cfg<D>;
+  auto kern = attn_fwd2_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((a.Nq + TQ - 1) / TQ, a.H, a.B);
+  cb_launch(kern, grid, FWD2_THREADS, C::SMEM_BYTES, stream, tq, tk, tv, a);
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
 // 4-D tensor map (dim, head, token, batch) over a strided bf16 view; box = {D, 1, rows, 1}
 int make_qkv_tmap(CUtensorMap* m, const void* ptr, long long sb, long long sn, long long sh, int B, int H, int N, int D,
                   int rows) {
@@ -358,7 +719,12 @@ extern "C" int cb_attention_fwd(const void* q, long long q_sb, long long q_sn, l
   a.o = (bf16*)o, a.o_sb = o_sb, a.o_sn = o_sn, a.o_sh = o_sh, a.lse = lse;
   a.B = B, a.H = H, a.Nq = Nq, a.Nk = Nk, a.scale_log2 = scale * LOG2E;
   cudaStream_t s = (cudaStream_t)stream;
-  return head_dim == 64 ? launch_fwd<64>(tq, tk, tv, a, s) : launch_fwd<32>(tq, tk, tv, a, s);
+  static const int gen = [] {  // CB_ATTN_FWD=1 selects the first-generation kernel (A/B measurements)
+    const char* e = getenv("CB_ATTN_FWD");
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  if (gen == 1) return head_dim == 64 ? launch_fwd<64>(tq, tk, tv, a, s) : launch_fwd<32>(tq, tk, tv, a, s);
+  return head_dim == 64 ? launch_fwd2<64>(tq, tk, tv, a, s) : launch_fwd2<32>(tq, tk, tv, a, s);
 }
 
 
@@ -710,6 +1076,411 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward, second generation (default).  Same tiling and MMAs as above (one CTA per 128-key tile, loop over 128-query
+// tiles, lanes = keys), re-plumbed so that nothing on the SM waits in lock step (profiles/r01_attention_clock_trace.md:
+// the first generation spent 3.8 k clocks per query tile in ONE serial chain of its eight compute warps -- TMEM loads,
+// 64 exponentials per thread, the dQ drain, TMEM / smem stores -- with the tensor pipe idle for most of it):
+//   * 512 threads: warpgroups 0 / 1 own the two 64-query HALVES of every tile with their own barriers
+//     (dp_full / sdp_free / ps_ready / pdk_done per half), so they drift apart and one half's exp2 phase runs under the
+//     other's TMEM traffic and barrier waits; S^T / dP^T (N = 64) and dV / dK are issued per half.  Each half is
+//     processed in two 32-query chunks (64 accumulator registers in flight, no spills) and its dS^T vectors are
+//     stored to shared memory as they are produced, so the generic->async proxy fence finds nothing in flight.
+//   * warpgroup 2 drains dQ (TMEM -> swizzled smem transposition -> coalesced fp32 red.global.add) off the critical
+//     path; at head_dim 32 the dQ accumulator is double buffered in TMEM, so dQ(i+1) is issued while dQ(i) drains.
+//   * dS^T in shared memory (the MN-major A operand of dQ = dS K) is double buffered by tile parity.
+//   * warpgroup 3: TMA producer warp (three Q / dO stages) and TWO MMA issuer warps -- one issues S^T / dP^T of the
+//     next tile the moment a half's registers are loaded, the other dV / dK per half and dQ per tile -- each running
+//     converged with one elected lane, so that the tcgen05 instructions go out back to back (the single `lane == 0`
+//     issuer of the first cut needed ~3 k clocks per query tile for its 32 MMAs + 9 commits and sat on the critical
+//     path together with the exposed TMA latency of a two-stage ring).  Registers: 2 x 192 + 64 + 64 (setmaxnreg).
+//   * the second half of a last query tile that holds no queries (Nq % 128 in 1..64) skips its arithmetic.
+// TMEM: S^T (2 x 64) | dP^T (2 x 64) | P^T (2 x 32 packed) | [dS^T (2 x 32 packed)] | dV (D) | dK (D) | dQ (D) [| dQ' (D)].
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD2_THREADS = 512;
+
+template <int D>
+struct Bwd2Cfg {
+  static constexpr int ROW_BYTES = D * 2;
+  static constexpr uint64_t SWZ = D == 64 ? UMMA_SW128 : UMMA_SW64;
+  static constexpr int GROUP_BYTES = 8 * ROW_BYTES;
+  static constexpr int TILE_BYTES = 128 * ROW_BYTES;
+  static constexpr int PS_BYTES = 128 * 128 * 2;  // one dS^T buffer: two 64-query chunks of 16 KB
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE_BYTES;
+  static constexpr int STAGES = 3;                           // Q / dO / per-query vector stages
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;
+  static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
+  static constexpr int OFF_DS = OFF_DO + STAGES * TILE_BYTES;  // 2 buffers (tile parity)
+  static constexpr int OFF_VEC = OFF_DS + 2 * PS_BYTES;        // lse / delta: [STAGES][2][128] floats
+  static constexpr int OFF_STG = OFF_VEC + STAGES * 2 * 128 * 4;  // dQ drain transposition: 4 warps x (32 rows x 64 B)
+  static constexpr int OFF_BAR = OFF_STG + 4 * 2048;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr bool DS_TMEM = D <= 32;  // dS^T as a TMEM A operand for dK (an smem A operand paces N = 32 MMAs at ~64 clk)
+  static constexpr bool DQ2 = D <= 32;      // two dQ accumulators
+  static constexpr int TM_S = 0, TM_DP = 128, TM_PT = 256, TM_DST = 320;
+  static constexpr int TM_DV = DS_TMEM ? 384 : 320, TM_DK = TM_DV + D, TM_DQ = TM_DV + 2 * D;
+  static_assert(TM_DQ + (DQ2 ? 2 : 1) * D <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(BWD2_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                 const AttnBwdArgs p) {
+  using C = Bwd2Cfg<D>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;    // [3] stages
+  uint64_t* qdo_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;      // [2] halves
+  uint64_t* dp_full = bars + 9;     // [2]
+  uint64_t* sdp_free = bars + 11;   // [2], 4 warp arrivals each
+  uint64_t* ps_ready = bars + 13;   // [2], 4 warp arrivals each
+  uint64_t* pdk_done = bars + 15;   // [2]: dV / dK MMAs of this half retired -> its P^T / dS^T TMEM columns are free
+  uint64_t* ds_free = bars + 17;    // [2] smem dS^T buffers (tile parity): dQ MMAs of that tile retired
+  uint64_t* dq_full = bars + 19;    // [2] dQ accumulators
+  uint64_t* dq_free = bars + 21;    // [2], 4 warp arrivals each
+  uint64_t* all_done = bars + 23;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* vec = reinterpret_cast<float*>(smem + C::OFF_VEC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_q = (p.Nq + 127) / 128;
+  const int last_halves = (p.Nq - (n_q - 1) * 128 + 63) >> 6;  // halves of the last query tile that hold queries (1 or 2)
+  long long* const trace = g_attn_trace;
+  const bool tron = trace != nullptr && lane == 0 && blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == gridDim.z / 2;
+  if (warp == 0) CB_TR(1000);
+
+  if (warp == 13) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1), mbar_init(all_done, 1);
+      for (int i = 0; i < C::STAGES; ++i) mbar_init(&qdo_full[i], 1), mbar_init(&qdo_empty[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1), mbar_init(&dp_full[i], 1), mbar_init(&sdp_free[i], 4), mbar_init(&ps_ready[i], 4);
+        mbar_init(&pdk_done[i], 1), mbar_init(&ds_free[i], 1), mbar_init(&dq_full[i], 1), mbar_init(&dq_free[i], 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q), tma_prefetch_desc(&tm_k), tma_prefetch_desc(&tm_v), tma_prefetch_desc(&tm_do);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // PDL: setup done, wait for the kernels that produce Q / K / V / dO before the first load
+  if (warp == 0) CB_TR(1001);
+
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");  // 128 x (2 x 192 + 64 + 64) == 64 K registers
+    if (warp == 12) {
+      // ------------------------------------------------ TMA producer
+      if (lane == 0) {
+        mbar_expect_tx(kv_full, 2 * C::TILE_BYTES);
+        tma_load_4d(smem + C::OFF_K, &tm_k, kv_full, 0, h, kv0, b);
+        tma_load_4d(smem + C::OFF_V, &tm_v, kv_full, 0, h, kv0, b);
+        for (int i = 0; i < n_q; ++i) {
+          const int s = i % C::STAGES;
+          mbar_wait(&qdo_empty[s], ((i / C::STAGES) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[s], 2 * C::TILE_BYTES + 1024);
+          tma_load_4d(smem + C::OFF_Q + s * C::TILE_BYTES, &tm_q, &qdo_full[s], 0, h, i * 128, b);
+          tma_load_4d(smem + C::OFF_DO + s * C::TILE_BYTES, &tm_do, &qdo_full[s], 0, h, i * 128, b);
+          const long long voff = ((long long)b * p.H + h) * p.NqP + i * 128;  // per-query vectors of this tile
+          bulk_load_1d(vec + s * 256, p.nl2 + voff, 512, &qdo_full[s]);
+          bulk_load_1d(vec + s * 256 + 128, p.dsc + voff, 512, &qdo_full[s]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 13) {
+      // ------------------------------------------------ MMA issuer A: S^T / dP^T of every half, as early as possible
+      // (whole warp converged, one elected lane issues: see attn_fwd2_kernel)
+      const bool leader = elect_one_sync() != 0;
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);  // S^T / dP^T of one half
+      const uint32_t k_base = smem_u32(smem + C::OFF_K);
+      const uint32_t v_base = smem_u32(smem + C::OFF_V);
+      const uint32_t q_base = smem_u32(smem + C::OFF_Q);
+      const uint32_t do_base = smem_u32(smem + C::OFF_DO);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % C::STAGES;
+        mbar_wait(&qdo_full[st], (i / C::STAGES) & 1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (i > 0) mbar_wait(&sdp_free[hf], (i - 1) & 1);  // warpgroup hf holds S^T / dP^T of tile i - 1 in registers
+          tcgen05_fence_after();
+          if (leader) {  // queries [64 hf, 64 hf + 64) of tile i: rows of the Q / dO tiles
+            const uint32_t qs = q_base + st * C::TILE_BYTES + hf * 8 * C::GROUP_BYTES;
+            const uint32_t dos = do_base + st * C::TILE_BYTES + hf * 8 * C::GROUP_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16_ss(tmem_base + C::TM_S + hf * 64, umma_smem_desc(k_base + kk * 32, 0, C::GROUP_BYTES, C::SWZ),
+                           umma_smem_desc(qs + kk * 32, 0, C::GROUP_BYTES, C::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16_ss(tmem_base + C::TM_DP + hf * 64, umma_smem_desc(v_base + kk * 32, 0, C::GROUP_BYTES, C::SWZ),
+                           umma_smem_desc(dos + kk * 32, 0, C::GROUP_BYTES, C::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+            umma_commit(&dp_full[hf]);  // one arrival for S^T and dP^T of this half
+          }
+          __syncwarp();
+        }
+        if (i < 24) CB_TR(32 * i + 16);
+      }
+    } else if (warp == 14) {
+      // ------------------------------------------------ MMA issuer B: dV / dK per half, then dQ of the tile
+      const bool leader = elect_one_sync() != 0;
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, D, false, true);   // dV, dK
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, true, true);    // dQ
+      const uint32_t k_base = smem_u32(smem + C::OFF_K);
+      const uint32_t q_base = smem_u32(smem + C::OFF_Q);
+      const uint32_t do_base = smem_u32(smem + C::OFF_DO);
+      const uint32_t ds_base0 = smem_u32(smem + C::OFF_DS);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % C::STAGES;
+        mbar_wait(&qdo_full[st], (i / C::STAGES) & 1);  // (long complete: the compute warps needed it; orders the TMA writes)
+        const uint32_t qs = q_base + st * C::TILE_BYTES;
+        const uint32_t dos = do_base + st * C::TILE_BYTES;
+        const uint32_t ds_base = ds_base0 + (i & 1) * C::PS_BYTES;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&ps_ready[hf], i & 1);
+          if (i < 24) CB_TR(32 * i + 17 + 2 * hf);
+          tcgen05_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {  // dV += P^T dO_i   (A = P^T from TMEM: 16 queries = 8 packed columns per step)
+              const int kk = hf * 4 + k4;
+              const uint64_t db = umma_smem_desc(dos + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+              umma_bf16_ts(tmem_base + C::TM_DV, tmem_base + C::TM_PT + kk * 8, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {  // dK += dS^T Q_i
+              const int kk = hf * 4 + k4;
+              const uint64_t db = umma_smem_desc(qs + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+              if constexpr (C::DS_TMEM) {
+                umma_bf16_ts(tmem_base + C::TM_DK, tmem_base + C::TM_DST + kk * 8, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+              } else {
+                const uint64_t da = umma_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, UMMA_SW128);
+                umma_bf16_ss(tmem_base + C::TM_DK, da, db, idesc_kv, (i > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&pdk_done[hf]);
+            if (hf == 1) umma_commit(&qdo_empty[st]);  // Q_i / dO_i (and the vectors) have no reader left
+          }
+          __syncwarp();
+          if (i < 24) CB_TR(32 * i + 18 + 2 * hf);
+        }
+        // dQ_i = dS K   (A = dS^T of both halves read MN-major from smem: M = queries contiguous)
+        int buf = 0;
+        if constexpr (C::DQ2) {
+          buf = i & 1;
+          if (i >= 2) mbar_wait(&dq_free[buf], ((i >> 1) & 1) ^ 1);  // tile i - 2 drained from this accumulator
+        } else {
+          if (i >= 1) mbar_wait(&dq_free[0], (i - 1) & 1);
+        }
+        if (i < 24) CB_TR(32 * i + 21);
+        tcgen05_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t da = umma_smem_desc(ds_base + kk * 2048, 16384, 1024, UMMA_SW128);
+            const uint64_t db = umma_smem_desc(k_base + kk * 2 * C::GROUP_BYTES, 0, C::GROUP_BYTES, C::SWZ);
+            umma_bf16_ss(tmem_base + C::TM_DQ + buf * D, da, db, idesc_dq, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&dq_full[buf]);
+          umma_commit(&ds_free[i & 1]);
+          if (i == n_q - 1) umma_commit(all_done);
+        }
+        __syncwarp();
+        if (i < 24) CB_TR(32 * i + 22);
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------ dQ drain warpgroup: lanes = query rows, D columns per warp
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    const int w4 = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
+    float* dq_g = p.dq_acc + ((long long)b * p.H + h) * p.Nq * D;
+    // The accumulator chunk (thread == row, 16 fp32) goes through a per-warp swizzled smem tile so that each fp32
+    // reduction instruction covers 8 rows x 64 contiguous bytes (whole sectors) instead of 32 rows x 16 bytes.
+    const uint32_t stg = smem_u32(smem + C::OFF_STG + w4 * 2048);
+    const int sub = lane >> 2, c16 = lane & 3;
+    for (int i = 0; i < n_q; ++i) {
+      int buf = 0;
+      uint32_t ph = i & 1;
+      if constexpr (C::DQ2) buf = i & 1, ph = (i >> 1) & 1;
+      mbar_wait(&dq_full[buf], ph);
+      if (warp == 8 && i < 24) CB_TR(32 * i + 24);
+      tcgen05_fence_after();
+      const int row0 = i * 128 + w4 * 32;  // first query row of this warp
+      if (row0 < p.Nq) {
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(lane_addr + C::TM_DQ + buf * D + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
+                         "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = k * 8 + sub;
+            float x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
+                         : "r"(stg + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4)));
+            const int q_row = row0 + rr;
+            if (q_row < p.Nq) red_add_v4f(dq_g + (long long)q_row * D + c * 16 + c16 * 4, x0, x1, x2, x3);
+          }
+          __syncwarp();
+        }
+      }
+      if (warp == 8 && i < 24) CB_TR(32 * i + 25);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_free[buf]);
+    }
+  } else {
+    // ------------------------------------------------ two compute warpgroups: half hf = 64 query columns of every tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    const int hf = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;  // key row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int i = 0; i < n_q; ++i) {
+      // the second half of a ragged last tile may hold no query at all: P^T = dS^T = 0 there by construction (padded
+      // vectors), so the TMEM loads and the arithmetic are skipped and zeros are stored
+      const bool live = !(i == n_q - 1 && hf >= last_halves);
+      const uint32_t nl_s32 = smem_u32(vec + (i % C::STAGES) * 256) + hf * 256;  // this half's 64 queries (16 float4)
+      const uint32_t ds_v32 = nl_s32 + 512;
+      const uint32_t ds_s32 = smem_u32(smem + C::OFF_DS + (i & 1) * C::PS_BYTES + hf * 16384);
+      const bool tri = (warp & 3) == 0 && i < 24;
+      const int tb = 32 * i + 8 * hf;
+      if (tri) CB_TR(tb + 0);
+      mbar_wait(&dp_full[hf], i & 1);                                // S^T and dP^T of this half (one commit covers both)
+      mbar_wait(&qdo_full[i % C::STAGES], (i / C::STAGES) & 1);      // the per-query vectors travelled with this stage
+      if (i >= 2) mbar_wait(&ds_free[i & 1], ((i >> 1) & 1) ^ 1);    // dQ (dK) of tile i - 2 have read this smem buffer
+      if (tri) CB_TR(tb + 1);
+      tcgen05_fence_after();
+      uint32_t pk[32], dsk[32];  // packed bf16 P^T and dS^T of this half
+      if (live) {
+        // two chunks of 32 queries: 64 accumulator registers in flight instead of 128 (no spills), and the dS^T
+        // vectors go to shared memory as they are produced, far ahead of the proxy fence below
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t vs[32], vd[32];
+          tmem_ld_32x32b_x32(lane_addr + C::TM_S + hf * 64 + c * 32, vs);
+          tmem_ld_32x32b_x32(lane_addr + C::TM_DP + hf * 64 + c * 32, vd);
+          tmem_ld_wait();
+          if (c == 1) {  // S^T / dP^T of this half are in registers: issuer A may overwrite them with tile i + 1
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sdp_free[hf]);
+            if (tri) CB_TR(tb + 3);
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 nl, dsv;  // explicit shared-memory loads (broadcast): a generic LD here serialises on its latency
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nl.x), "=f"(nl.y), "=f"(nl.z), "=f"(nl.w) : "r"(nl_s32 + (c * 8 + g) * 16));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dsv.x), "=f"(dsv.y), "=f"(dsv.z), "=f"(dsv.w) : "r"(ds_v32 + (c * 8 + g) * 16));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * g + 0]), p.scale_log2, nl.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vs[4 * g + 1]), p.scale_log2, nl.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(vs[4 * g + 2]), p.scale_log2, nl.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(vs[4 * g + 3]), p.scale_log2, nl.w));
+            const int o = c * 16 + 2 * g;
+            pk[o] = pack_bf16(p0, p1);
+            pk[o + 1] = pack_bf16(p2, p3);
+            dsk[o] = pack_bf16(p0 * fmaf(__uint_as_float(vd[4 * g + 0]), p.scale, -dsv.x),
+                               p1 * fmaf(__uint_as_float(vd[4 * g + 1]), p.scale, -dsv.y));
+            dsk[o + 1] = pack_bf16(p2 * fmaf(__uint_as_float(vd[4 * g + 2]), p.scale, -dsv.z),
+                                   p3 * fmaf(__uint_as_float(vd[4 * g + 3]), p.scale, -dsv.w));
+          }
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {  // dS^T -> smem: dQ = dS K reads it transposed (MN-major A)
+            const int vcol = c * 4 + v4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s32 + sw128_vec_offset(r, vcol)), "r"(dsk[4 * vcol]),
+                         "r"(dsk[4 * vcol + 1]), "r"(dsk[4 * vcol + 2]), "r"(dsk[4 * vcol + 3])
+                         : "memory");
+          }
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 32; ++g) pk[g] = 0u, dsk[g] = 0u;
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdp_free[hf]);
+#pragma unroll
+        for (int vcol = 0; vcol < 8; ++vcol)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s32 + sw128_vec_offset(r, vcol)), "r"(0u) : "memory");
+      }
+      if (tri) CB_TR(tb + 4);
+      if (i > 0) mbar_wait(&pdk_done[hf], (i - 1) & 1);  // this half's P^T / dS^T TMEM columns are free
+      if (tri) CB_TR(tb + 5);
+      tcgen05_fence_after();
+      // P^T (and dS^T for head_dim 32) -> TMEM as packed bf16: this half's 64 queries = 32 columns
+      tmem_st_32x32b_x32(lane_addr + C::TM_PT + hf * 32, pk);
+      if constexpr (C::DS_TMEM) tmem_st_32x32b_x32(lane_addr + C::TM_DST + hf * 32, dsk);
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      if (tri) CB_TR(tb + 6);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ps_ready[hf]);
+    }
+    if (warp == 0) CB_TR(1002);
+    mbar_wait(all_done, 0);
+    tcgen05_fence_after();
+
+    // dK / dV epilogue: lanes = key rows, this warpgroup takes D/2 columns of each
+    const int kv_row = kv0 + r;
+    bf16* dk_ptr = p.dk + (long long)b * p.dk_sb + (long long)kv_row * p.dk_sn + (long long)h * p.dk_sh + hf * (D / 2);
+    bf16* dv_ptr = p.dv + (long long)b * p.dv_sb + (long long)kv_row * p.dv_sn + (long long)h * p.dv_sh + hf * (D / 2);
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t a[16], v[16];
+      tmem_ld_32x32b_x16(lane_addr + C::TM_DK + hf * (D / 2) + c * 16, a);
+      tmem_ld_32x32b_x16(lane_addr + C::TM_DV + hf * (D / 2) + c * 16, v);
+      tmem_ld_wait();
+      if (kv_row < p.Nk) {
+        uint4 w0 = make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                              pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
+        uint4 w1 = make_uint4(pack_bf16(__uint_as_float(a[8]), __uint_as_float(a[9])), pack_bf16(__uint_as_float(a[10]), __uint_as_float(a[11])),
+                              pack_bf16(__uint_as_float(a[12]), __uint_as_float(a[13])), pack_bf16(__uint_as_float(a[14]), __uint_as_float(a[15])));
+        reinterpret_cast<uint4*>(dk_ptr + c * 16)[0] = w0;
+        reinterpret_cast<uint4*>(dk_ptr + c * 16)[1] = w1;
+        uint4 x0 = make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                              pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+        uint4 x1 = make_uint4(pack_bf16(__uint_as_float(v[8]), __uint_as_float(v[9])), pack_bf16(__uint_as_float(v[10]), __uint_as_float(v[11])),
+                              pack_bf16(__uint_as_float(v[12]), __uint_as_float(v[13])), pack_bf16(__uint_as_float(v[14]), __uint_as_float(v[15])));
+        reinterpret_cast<uint4*>(dv_ptr + c * 16)[0] = x0;
+        reinterpret_cast<uint4*>(dv_ptr + c * 16)[1] = x1;
+      }
+    }
+    if (warp == 0) CB_TR(1003);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Per-query vectors of the backward, 8 lanes per (b, h, q) row, 16-byte loads:
 //   dsc[bh, q] = scale * sum_d O[b,q,h,d] * dO[b,q,h,d]      nl2[bh, q] = -lse[b,h,q] * log2(e)
 // rows are padded to NqP = 128 * ceil(Nq / 128) entries (nl2 = -inf -> P = 0, dsc = 0) so that the main kernel can
@@ -785,14 +1556,29 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
       a.NqP, a.scale);
   CB_LAUNCH_CHECK();
   CB_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)rows * D * sizeof(float), stream));
-  auto kern = attn_bwd_kernel<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static const int gen = [] {  // CB_ATTN_BWD=1 selects the first-generation kernel (A/B measurements)
+    const char* e = getenv("CB_ATTN_BWD");
+    return e != nullptr ? atoi(e) : 2;
+  }();
   dim3 grid((a.Nk + 127) / 128, a.H, a.B);
-  cb_launch(kern, grid, BWD_THREADS, C::SMEM_BYTES, stream, tq, tk, tv, tdo, a);
+  if (gen == 1) {
+    auto kern = attn_bwd_kernel<D>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      attr_set = true;
+    }
+    cb_launch(kern, grid, BWD_THREADS, C::SMEM_BYTES, stream, tq, tk, tv, tdo, a);
+  } else {
+    using C2 = Bwd2Cfg<D>;
+    auto kern = attn_bwd2_kernel<D>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
+      attr_set = true;
+    }
+    cb_launch(kern, grid, BWD2_THREADS, C2::SMEM_BYTES, stream, tq, tk, tv, tdo, a);
+  }
   CB_LAUNCH_CHECK();
   const long long vecs = rows * (D / 8);
   cb_launch(attn_dq_convert_kernel<D>, (unsigned)((vecs + 255) / 256), 256, 0, stream, a.dq_acc, dq, dq_sb, dq_sn, dq_sh, a.B,

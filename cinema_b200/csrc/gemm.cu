@@ -109,8 +109,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     else tmem_alloc(tmem_slot, C::TMEM_COLS);
   }
   tcgen05_fence_before();
+  __syncthreads();                     // this CTA: barrier words and the TMEM slot written by warp 1 are visible
   if constexpr (PAIR) cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
-  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // barriers, TMEM and descriptors are set up: now wait for the producer kernels of A / B / residual

@@ -228,6 +228,12 @@ int cb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, long 
  * in the tail of its predecessor. */
 int cb_set_pdl(int enabled);
 
+/* Diagnostics: register a DEVICE buffer of at least 1024 long long (or NULL to switch off, the default).  While set, one
+ * CTA in the middle of the grid of every second-generation attention launch stamps clock64() at the phase boundaries of
+ * its softmax / compute warps and of its MMA-issuing warp (slot layout and reader: tools/attn_trace.py).  This is how
+ * profiles/r0x_attention_clock_trace.md is produced; it is not part of any product path. */
+int cb_attention_trace(long long* device_buf);
+
 #ifdef __cplusplus
 }
 #endif
