@@ -66,14 +66,6 @@ struct FwdCfg {
   static constexpr int TMEM_O = 384;                          // column of O0; O1 at +D
 };
 
-// 1-D bulk copy global -> shared, completion (bytes) on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // element (row, col) of a K-major 128B-swizzled [128 x 64] bf16 chunk -> byte offset of its 16-byte vector
 __device__ __forceinline__ uint32_t sw128_vec_offset(int row, int vec /*0..7*/) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((vec ^ (row & 7)) << 4));

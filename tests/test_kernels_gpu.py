@@ -302,6 +302,18 @@ def _torch_patchify(image, patch):
     return x.reshape(b, math.prod(grid), math.prod(patch) * c)
 
 
+def _torch_unpatchify(tokens, patch, grid, c):
+    """inverse of _torch_patchify: (B, prod(grid), prod(patch) * C) channel fastest -> (B, C, *spatial)."""
+    n = len(patch)
+    b = tokens.shape[0]
+    x = tokens.reshape(b, *grid, *patch, c)
+    perm = [0, 2 * n + 1]
+    for i in range(n):
+        perm += [1 + i, 1 + n + i]
+    x = x.permute(*perm).contiguous()
+    return x.reshape(b, c, *[g_ * p_ for g_, p_ in zip(grid, patch)])
+
+
 @pytest.mark.parametrize("shape,patch", [((2, 1, 192, 192, 16), (16, 16, 1)), ((3, 1, 256, 256), (16, 16)),
                                          ((2, 3, 8, 12), (2, 4)), ((1, 2, 4, 4, 2, 6), (2, 2, 1, 3)),
                                          ((2, 128, 24, 24, 16), (2, 2, 1))])
@@ -348,6 +360,43 @@ def test_gather_scatter_patches(chan_last_mem, chan_last_order):
     for a, p in enumerate(patch):
         vis = vis.repeat_interleave(p, dim=2 + a)
     assert torch.equal(dst, x * vis)
+
+
+@pytest.mark.parametrize("t,c,f,grid,patch,chan_last", [
+    (576, 128, (2, 2), (1, 1), (2, 2), True), (576, 128, (2, 2), (1, 1), (2, 2), False),
+    (576, 64, (4, 4), (1, 1), (4, 4), False), (576, 64, (4, 4), (2, 2), (2, 2), False), (576, 64, (4, 4), (2, 2), (2, 2), True),
+    (1000, 128, (2, 2, 1), (1, 1, 1), (2, 2, 1), True), (1000, 64, (4, 4, 1), (2, 2, 1), (2, 2, 1), False),
+    (37, 64, (4, 4, 1), (1, 1, 1), (4, 4, 1), False), (5, 32, (2, 2), (1, 1), (2, 2), False),
+])
+def test_token_major_patch_rows_bulk_copy_path(t, c, f, grid, patch, chan_last):
+    """The stem's token-major sources ((T, C, *f) fp32 views of [T][positions][C] memory, channel stride 1) take the
+    bulk-copy staged kernels (cp.async.bulk into shared memory, permutation in shared memory, bulk reduce-add back):
+    bit-exact against a plain torch restatement of gather_patches / scatter_patches, overwrite and accumulate, bf16 and
+    fp32 rows.  The last case (C = 32: block of 128 elements) falls back to the generic kernel and must agree too."""
+    g = torch.Generator(device=DEV).manual_seed(t + c)
+    mem = torch.randn(t, math.prod(f), c, device=DEV, generator=g)                 # [T][positions][C]
+    src = mem.view(t, *f, c).permute(0, len(f) + 1, *range(1, len(f) + 1))         # (T, C, *f), channel stride 1
+    assert src.stride(1) == 1
+    r, e = math.prod(grid), math.prod(patch) * c
+    out = torch.empty(t * r, e, device=DEV, dtype=torch.bfloat16)
+    _C.gather_patches(src, grid, patch, None, chan_last, out)
+    tok = _torch_patchify(src.contiguous(), patch)                                  # (T, R, prod(patch) * C) channel fastest
+    if not chan_last:
+        tok = tok.reshape(t, r, math.prod(patch), c).transpose(2, 3)
+    ref = tok.reshape(t * r, e)
+    assert torch.equal(out, ref.to(torch.bfloat16))
+    for rows in (out, ref.contiguous()):                                            # bf16 rows and fp32 rows
+        for accumulate in (False, True):
+            base = torch.randn(t, math.prod(f), c, device=DEV, generator=g)
+            dmem = base.clone()
+            dst = dmem.view(t, *f, c).permute(0, len(f) + 1, *range(1, len(f) + 1))
+            _C.scatter_patches(rows, dst, grid, patch, None, chan_last, accumulate=accumulate)
+            want = rows.float().reshape(t, r, -1)
+            if not chan_last:
+                want = want.reshape(t, r, c, math.prod(patch)).transpose(2, 3).reshape(t, r, -1)
+            img = _torch_unpatchify(want, patch, grid, c)                           # (T, C, *f)
+            want_mem = img.permute(0, *range(2, len(f) + 2), 1).reshape(t, math.prod(f), c)
+            assert torch.equal(dmem, base + want_mem if accumulate else want_mem)
 
 
 # ----------------------------------------------------------------------------- loss
