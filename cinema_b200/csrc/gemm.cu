@@ -123,7 +123,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // (producer and MMA issuer run as converged warps with one elected lane: under `lane == 0` nvcc wraps every TMA /
+    // tcgen05 instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and rebuilds its operands in front of it --
+    // ~67 clocks per instruction measured in the attention kernels, which short-K GEMMs cannot hide)
+    const bool leader = elect_one_sync() != 0;
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < items; item += n_workers) {
@@ -139,6 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
+          if (leader) {
           // pair: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
           if (!PAIR || cta_rank == 0) mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES * CTAS);
           if constexpr (CONV) {
@@ -160,6 +165,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int j = 0; j < BN / CTAS / 64; ++j)
               tma_load_2d_g<CTAS>(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
           }
+          }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -170,7 +177,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    const bool leader = elect_one_sync() != 0;
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -186,23 +194,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t b_base = a_base + C::A_BYTES;
+          if (leader) {
+            const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint32_t b_base = a_base + C::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_smem_desc(a_base + k * 2048, 8192, 1024, UMMA_SW128)
-                                     : umma_smem_desc(a_base + k * 32, 0, 1024, UMMA_SW128);
-            const uint64_t db = B_MN ? umma_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_SW128)
-                                     : umma_smem_desc(b_base + k * 32, 0, 1024, UMMA_SW128);
-            umma_bf16_ss_g<CTAS>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? umma_smem_desc(a_base + k * 2048, 8192, 1024, UMMA_SW128)
+                                       : umma_smem_desc(a_base + k * 32, 0, 1024, UMMA_SW128);
+              const uint64_t db = B_MN ? umma_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_SW128)
+                                       : umma_smem_desc(b_base + k * 32, 0, 1024, UMMA_SW128);
+              umma_bf16_ss_g<CTAS>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_g<CTAS>(&empty_bar[stage]);  // smem slot (of both CTAs) reusable once these MMAs retire
+            if (kb + 1 == kb1) umma_commit_g<CTAS>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
           }
-          umma_commit_g<CTAS>(&empty_bar[stage]);  // smem slot (of both CTAs) reusable once these MMAs retire
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_g<CTAS>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -37,3 +37,20 @@ with np.errstate(over="ignore"):
     approx = 1 / (1 + np.exp2(xs * p))
 exact = 0.5 * (1 + erf(xs.astype(np.float64) / np.sqrt(2)))
 print("float32 check on [-12, 12]: max |Phi err|", np.abs(approx - exact).max(), " max |gelu err|", np.abs(xs * (approx - exact)).max())
+
+# --check-grad: the tanh form used by gelu_grad_fast (Q = -ln2/2 * P) over every bf16 input in [-30, 30], tanh.approx
+# modelled at its worst-case relative error 2^-11
+q = (c * 0.5).astype(np.float32)
+print("tanh-form coefficients (gelu_grad_fast)", [f"{v:.9g}" for v in q])
+u16 = np.arange(0, 65536, dtype=np.uint32)
+xb = (u16 << 16).view(np.float32)
+xb = xb[np.isfinite(xb) & (np.abs(xb) <= 30)]
+xd = xb.astype(np.float64)
+gp = 0.5 * (1 + erf(xd / np.sqrt(2))) + xd * np.exp(-0.5 * xd ** 2) / np.sqrt(2 * np.pi)
+x2 = xb * xb
+qq = q[4]
+for k in (3, 2, 1, 0):
+    qq = qq * x2 + q[k]
+phi_t = 0.5 + 0.5 * np.tanh((xb * qq).astype(np.float64)) * (1 + 2.0 ** -11)
+gq = phi_t + xd * 0.3989422804014327 * np.exp2(-0.72134752044448170 * xd ** 2)
+print("GELU' (tanh form): max abs err", np.abs(gq - gp).max(), " rms", np.sqrt(((gq - gp) ** 2).mean()))
