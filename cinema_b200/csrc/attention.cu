@@ -1105,8 +1105,8 @@ struct Bwd2Cfg {
   static constexpr int OFF_DO = OFF_Q + STAGES * TILE_BYTES;
   static constexpr int OFF_DS = OFF_DO + STAGES * TILE_BYTES;  // 2 buffers (tile parity)
   static constexpr int OFF_VEC = OFF_DS + 2 * PS_BYTES;        // lse / delta: [STAGES][2][128] floats
-  static constexpr int OFF_STG = OFF_VEC + STAGES * 2 * 128 * 4;  // dQ drain transposition: 4 warps x (32 rows x 64 B)
-  static constexpr int OFF_BAR = OFF_STG + 4 * 2048;
+  static constexpr int OFF_STG = (OFF_VEC + STAGES * 2 * 128 * 4 + 1023) / 1024 * 1024;  // dQ drain: 4 warps x (32 rows x 128 B)
+  static constexpr int OFF_BAR = OFF_STG + 4 * 4096;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr bool DS_TMEM = D <= 32;  // dS^T as a TMEM A operand for dK (an smem A operand paces N = 32 MMAs at ~64 clk)
   static constexpr bool DQ2 = D <= 32;      // two dQ accumulators
@@ -1120,7 +1120,7 @@ template <int D>
 __global__ void __launch_bounds__(BWD2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                 const AttnBwdArgs p) {
+                 const __grid_constant__ CUtensorMap tm_dq, const AttnBwdArgs p) {
   using C = Bwd2Cfg<D>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -1301,14 +1301,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else if (warp >= 8) {
     // ------------------------------------------------ dQ drain warpgroup: lanes = query rows, D columns per warp
+    // TMEM -> registers -> a 128B-swizzled [32 rows x 32 fp32] staging tile per warp -> ONE bulk-tensor reduce-add per
+    // 32 columns (cp.reduce.async.bulk.tensor, fp32 add in L2).  The first cut drained with red.global.add.v4 from the
+    // LSU, which retires ~12 B per clock and SM (2.6 k clocks per 128 x 64 tile: it set the pace of the head_dim 64
+    // kernel, whose dQ accumulator cannot be double buffered); the TMA unit takes the tile off the SM in one
+    // instruction, and the 3-D tensor map (dim, query, batch * head) clips the ragged last query tile by itself.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int w4 = warp & 3;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
-    float* dq_g = p.dq_acc + ((long long)b * p.H + h) * p.Nq * D;
-    // The accumulator chunk (thread == row, 16 fp32) goes through a per-warp swizzled smem tile so that each fp32
-    // reduction instruction covers 8 rows x 64 contiguous bytes (whole sectors) instead of 32 rows x 16 bytes.
-    const uint32_t stg = smem_u32(smem + C::OFF_STG + w4 * 2048);
-    const int sub = lane >> 2, c16 = lane & 3;
+    uint8_t* stg = smem + C::OFF_STG + w4 * 4096;
+    const uint32_t stg32 = smem_u32(stg);
+    const int bh = b * p.H + h;
+    if (warp == 8 && lane == 0) tma_prefetch_desc(&tm_dq);
     for (int i = 0; i < n_q; ++i) {
       int buf = 0;
       uint32_t ph = i & 1;
@@ -1319,34 +1323,39 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int row0 = i * 128 + w4 * 32;  // first query row of this warp
       if (row0 < p.Nq) {
 #pragma unroll
-        for (int c = 0; c < D / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(lane_addr + C::TM_DQ + buf * D + c * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)),
-                         "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                         : "memory");
+        for (int half = 0; half < D / 32; ++half) {
+          if (lane == 0) bulk_wait_group_read0();  // the previous reduce has read the staging tile
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rr = k * 8 + sub;
-            float x0, x1, x2, x3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
-                         : "r"(stg + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4)));
-            const int q_row = row0 + rr;
-            if (q_row < p.Nq) red_add_v4f(dq_g + (long long)q_row * D + c * 16 + c16 * 4, x0, x1, x2, x3);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(lane_addr + C::TM_DQ + buf * D + half * 32 + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)  // row = lane, 16-byte chunk (c * 4 + j) of the 128-byte row, 128B swizzle
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg32 + lane * 128 + (((c * 4 + j) ^ (lane & 7)) << 4)),
+                           "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                           : "memory");
           }
+          if (half == D / 32 - 1) {  // the accumulator is in registers / shared memory: hand it back to the MMA warp
+            tcgen05_fence_before();
+          }
+          fence_proxy_async_smem();
           __syncwarp();
+          if (lane == 0) {
+            if (half == D / 32 - 1) mbar_arrive(&dq_free[buf]);
+            tma_reduce_add_3d(&tm_dq, stg, half * 32, row0, bh);
+            bulk_commit_group();
+          }
         }
+      } else {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_free[buf]);
       }
       if (warp == 8 && i < 24) CB_TR(32 * i + 25);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_free[buf]);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // reductions complete before the CTA retires
   } else {
     // ------------------------------------------------ two compute warpgroups: half hf = 64 query columns of every tile
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
@@ -1473,46 +1482,47 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 }
 
-// Per-query vectors of the backward, 8 lanes per (b, h, q) row, 16-byte loads:
+// Per-query vectors of the backward, D / 8 lanes per (b, q, h) row, 16-byte loads:
 //   dsc[bh, q] = scale * sum_d O[b,q,h,d] * dO[b,q,h,d]      nl2[bh, q] = -lse[b,h,q] * log2(e)
 // rows are padded to NqP = 128 * ceil(Nq / 128) entries (nl2 = -inf -> P = 0, dsc = 0) so that the main kernel can
-// fetch whole 128-query vectors with one bulk copy each.
+// fetch whole 128-query vectors with one bulk copy each.  Threads walk the rows in MEMORY order (batch, query, head):
+// the heads of one query are adjacent in the projection output, so a warp reads 512 contiguous bytes of O and of dO
+// (the first cut walked (batch, head, query) and touched 64 useful bytes per kilobyte: 2.0 TB/s); the two small outputs
+// are written transposed.
 template <int D>
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sn, long long o_sh,
                                   const bf16* __restrict__ d_o, long long do_sb, long long do_sn, long long do_sh,
                                   const float* __restrict__ lse, float* __restrict__ nl2, float* __restrict__ dsc, int B,
                                   int H, int Nq, int NqP, float scale) {
   pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
+  constexpr int LPR = D / 8;  // lanes per row
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long row = gid >> 3;  // over B * H * NqP
-  const int sub = (int)(gid & 7);
+  const long long row = gid / LPR;  // over B * NqP * H, head fastest
+  const int sub = (int)(gid % LPR);
   const long long total = (long long)B * H * NqP;
   float acc = 0.f;
-  const int q = (int)(row % NqP);
-  const long long bh = row / NqP;
+  const int h = (int)(row % H);
+  const int q = (int)((row / H) % NqP);
+  const int b = (int)(row / ((long long)H * NqP));
   const bool live = row < total && q < Nq;
   if (live) {
-    const int h = (int)(bh % H);
-    const int b = (int)(bh / H);
-    const bf16* op = o + b * o_sb + (long long)q * o_sn + (long long)h * o_sh;
-    const bf16* dp = d_o + b * do_sb + (long long)q * do_sn + (long long)h * do_sh;
-    for (int c = sub * 8; c < D; c += 64) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(op + c));
-      const uint4 g = __ldg(reinterpret_cast<const uint4*>(dp + c));
-      const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
+    const bf16* op = o + b * o_sb + (long long)q * o_sn + (long long)h * o_sh + sub * 8;
+    const bf16* dp = d_o + b * do_sb + (long long)q * do_sn + (long long)h * do_sh + sub * 8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(op));
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dp));
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = unpack_bf16(au[k]), y = unpack_bf16(gu[k]);
-        acc += x.x * y.x + x.y * y.y;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16(au[k]), y = unpack_bf16(gu[k]);
+      acc += x.x * y.x + x.y * y.y;
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+#pragma unroll
+  for (int m = 1; m < LPR; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
   if (row < total && sub == 0) {
-    dsc[row] = live ? acc * scale : 0.f;
-    nl2[row] = live ? -lse[bh * Nq + q] * LOG2E : -INFINITY;
+    const long long out = ((long long)b * H + h) * NqP + q;
+    dsc[out] = live ? acc * scale : 0.f;
+    nl2[out] = live ? -lse[((long long)b * H + h) * Nq + q] * LOG2E : -INFINITY;
   }
 }
 
@@ -1543,7 +1553,7 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
   using C = BwdCfg<D>;
   const long long rows = (long long)a.B * a.H * a.Nq;
   const long long rows_p = (long long)a.B * a.H * a.NqP;
-  cb_launch(attn_delta_kernel<D>, (unsigned)((rows_p * 8 + 255) / 256), 256, 0, stream, 
+  cb_launch(attn_delta_kernel<D>, (unsigned)((rows_p * (D / 8) + 255) / 256), 256, 0, stream, 
       o, o_sb, o_sn, o_sh, d_o, do_sb, do_sn, do_sh, lse, const_cast<float*>(a.nl2), const_cast<float*>(a.dsc), a.B, a.H, a.Nq,
       a.NqP, a.scale);
   CB_LAUNCH_CHECK();
@@ -1569,7 +1579,15 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
       CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
       attr_set = true;
     }
-    cb_launch(kern, grid, BWD2_THREADS, C2::SMEM_BYTES, stream, tq, tk, tv, tdo, a);
+    // dq_acc [B * H, Nq, D] fp32 as a 3-D tensor: box = 32 columns x 32 rows, 128B swizzle (the drain's staging tile)
+    CUtensorMap tdq;
+    {
+      uint64_t dims[3] = {(uint64_t)D, (uint64_t)a.Nq, (uint64_t)a.B * a.H};
+      uint64_t strides[2] = {(uint64_t)D * 4, (uint64_t)a.Nq * D * 4};
+      uint32_t box[3] = {32, 32, 1};
+      if (int rc = cb_make_tmap_nd_f32(&tdq, a.dq_acc, 3, dims, strides, box, 128)) return rc;
+    }
+    cb_launch(kern, grid, BWD2_THREADS, C2::SMEM_BYTES, stream, tq, tk, tv, tdo, tdq, a);
   }
   CB_LAUNCH_CHECK();
   const long long vecs = rows * (D / 8);

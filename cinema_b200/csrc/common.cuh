@@ -209,6 +209,13 @@ __device__ __forceinline__ void bulk_reduce_add_f32_1d(float* gdst, const void* 
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// shared -> global fp32 reduce-add of one 3-D tensor-map box (rows outside the tensor are clipped by the TMA unit)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -445,3 +452,6 @@ int cb_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
 // generic rank-N bf16 tensor map (dims innermost first; strides for dims 1.. in bytes)
 int cb_make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes);
+// the same for an fp32 tensor (strides in bytes)
+int cb_make_tmap_nd_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, int swizzle_bytes);
