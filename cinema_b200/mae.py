@@ -304,7 +304,15 @@ def _grad_stage_done(model, stage: str) -> None:
 
 
 def encoder_stage_points(depth: int) -> list[int]:
-    """Encoder block indices (descending) after whose backward a gradient stage is reported: quarters of the stack."""
+    """Encoder block indices (descending) after whose backward a gradient stage is reported: quarters of the stack.
+    (Finer cuts -- down to block 1, so that only block 0 + stems + embeddings remain for the bucket that follows the
+    backward -- measured the same at 2 x B200: 26.16 / 26.23 / 26.30 / 26.31 ms per step for the points {6} / {9,6,3} /
+    {9,6,3,1} / {8,4,1}, 26.54 ms without any overlap, profiles/r02_scaling.md.)"""
+    import os
+
+    env = os.environ.get("CB_STAGE_POINTS")  # e.g. "6" or "9,6,3": override for scaling experiments
+    if env is not None:
+        return sorted({int(x) for x in env.split(",") if x.strip() and 0 < int(x) < depth}, reverse=True)
     return sorted({depth * 3 // 4, depth // 2, depth // 4} - {0}, reverse=True)
 
 

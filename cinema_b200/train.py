@@ -216,6 +216,20 @@ class MAETrainer:
             ids = {id(p) for p in covered}
             self._rest_ranges = self.arena.ranges_of([p for p in self.arena.params if id(p) not in ids])
             model._grad_stage_hook = self._on_stage
+        # Optional experiment (CB_NCCL_BG_CTAS=n > 0): overlapped buckets go through a SECOND communicator limited to n
+        # CTAs, the tail bucket stays on the default one.  Measured at 2 x B200 (profiles/r02_scaling.md): 26.69 ms with
+        # n = 4 and 29.21 ms with n = 2 against 26.09 ms on the default communicator -- the throttled all-reduce of the
+        # last overlapped bucket no longer finishes under the backward -- so it is OFF by default.
+        self._bg_pg = None
+        bg_ctas = int(os.environ.get("CB_NCCL_BG_CTAS", "0"))
+        if self.overlap and self.world > 1 and bg_ctas > 0 and self.arena.device.type == "cuda" and self.pg is None:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = bg_ctas
+                opts.config.min_ctas = 1
+                self._bg_pg = dist.new_group(backend="nccl", pg_options=opts)
+            except Exception:  # noqa: BLE001 -- older torch / non-NCCL backends: fall back to the default communicator
+                self._bg_pg = None
         self.use_graph = use_cuda_graph and self.arena.device.type == "cuda"
         self.graph_warmup = graph_warmup
         self._n_calls = 0
@@ -277,12 +291,14 @@ class MAETrainer:
             ready.record(self._copy_stream)
         self._prefetched = (batch, self._staged, ready)
 
-    def _reduce_async(self, ranges) -> None:
+    def _reduce_async(self, ranges, tail: bool = False) -> None:
         """Hand flat gradient ranges to NCCL on its own stream (ordered after everything queued on the current stream so
-        far); the caller joins with ``_join_reduces`` before the optimiser reads the gradients."""
+        far); the caller joins with ``_join_reduces`` before the optimiser reads the gradients.  ``tail``: the bucket
+        that follows the backward (full-speed communicator); the others use the CTA-limited background communicator."""
         if self.world > 1:
+            pg = self.pg if (tail or self._bg_pg is None) else self._bg_pg
             for s, e in ranges:
-                self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                self._pending.append(dist.all_reduce(self.arena.gflat[s:e], op=dist.ReduceOp.SUM, group=pg, async_op=True))
 
     def _join_reduces(self) -> None:
         for w in self._pending:
@@ -319,7 +335,7 @@ class MAETrainer:
         self._pending = []
         self._compute()
         if self.overlap:  # the rest of the arena, then join every bucket before the optimiser reads the gradients
-            self._reduce_async(self._rest_ranges)
+            self._reduce_async(self._rest_ranges, tail=True)
             self._join_reduces()
 
     def _replay_fwd_bwd(self) -> None:
@@ -327,9 +343,10 @@ class MAETrainer:
             self._g_fb.replay()
             return
         self._pending = []
-        for g, ranges in self._fb_segments:
+        last = len(self._fb_segments) - 1
+        for j, (g, ranges) in enumerate(self._fb_segments):
             g.replay()
-            self._reduce_async(ranges)
+            self._reduce_async(ranges, tail=j == last)
         self._join_reduces()
 
     def _reduce(self) -> None:
