@@ -33,6 +33,7 @@ _SIGNATURES = {
     "cb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cb_set_pdl": (c_int, [c_int]),
     "cb_attention_trace": (c_int, [c_void_p]),
+    "cb_scale_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -363,6 +364,21 @@ def scale_cast(src: torch.Tensor, dst: torch.Tensor, scale_dev: torch.Tensor | N
         assert scale_dev is not None and scale_dev.numel() * group == src.numel()
     _check(lib().cb_scale_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _ptr(scale_dev), float(scale), int(group),
                                     _stream()), "scale_cast")
+
+
+_RAW_DT = {torch.uint8: 2, torch.int16: 3, torch.uint16: 4, torch.float32: 1}
+
+
+def scale_intensity(raw: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (B, ...) fp32 = (raw - lo[b]) / (hi[b] - lo[b]) per sample (0 for a constant sample): MONAI ScaleIntensity(0, 1)
+    on the device in one pass.  raw: uint8 / int16 / uint16 / float32, contiguous; lo / hi: fp32 (B,)."""
+    assert raw.dtype in _RAW_DT and raw.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    assert out.shape == raw.shape and lo.dtype == torch.float32 and hi.dtype == torch.float32
+    b = raw.shape[0]
+    assert lo.numel() == b and hi.numel() == b and lo.is_contiguous() and hi.is_contiguous()
+    _check(lib().cb_scale_intensity(_ptr(raw), _RAW_DT[raw.dtype], _ptr(lo), _ptr(hi), _ptr(out), b, raw.numel() // b,
+                                    _stream()), "scale_intensity")
+    return out
 
 
 def mae_loss_finalize(acc: torch.Tensor, sq_count, patch_count, out: torch.Tensor, scales: torch.Tensor) -> None:

@@ -750,6 +750,7 @@ struct AttnBwdArgs {
   long long dv_sb, dv_sn, dv_sh;
   int B, H, Nq, Nk;
   float scale, scale_log2;
+  int token;  // second-generation kernel: alternate the exp2 section between the two compute warpgroups
 };
 
 template <int D>
@@ -1362,6 +1363,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int hf = warp >> 2;
     const int r = (warp & 3) * 32 + lane;  // key row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    // The exp2-heavy section is handed back and forth between the two warpgroups with named barriers 1 / 2 (256 threads:
+    // one warpgroup syncs, the other arrives), half 0 first.  Left alone the halves run in lock step -- both in the
+    // MUFU-bound section (1.6 k clocks for the pair), then both in barrier waits / TMEM loads / stores with the MUFU pipe
+    // idle (0.85 k); with the token they settle half an iteration apart and one half's arithmetic runs under the
+    // other's memory phases.  CB_ATTN_BWD_TOKEN=0 (AttnBwdArgs::token) switches it off for A/B measurements.
+    const bool token = p.token != 0;
+    if (token && hf == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
     for (int i = 0; i < n_q; ++i) {
       // the second half of a ragged last tile may hold no query at all: P^T = dS^T = 0 there by construction (padded
       // vectors), so the TMEM loads and the arithmetic are skipped and zeros are stored
@@ -1381,18 +1389,26 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (live) {
         // two chunks of 32 queries: 64 accumulator registers in flight instead of 128 (no spills), and the dS^T
         // vectors go to shared memory as they are produced, far ahead of the proxy fence below
+        uint32_t vs_all[2][32], vd_all[2][32];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t vs[32], vd[32];
-          tmem_ld_32x32b_x32(lane_addr + C::TM_S + hf * 64 + c * 32, vs);
-          tmem_ld_32x32b_x32(lane_addr + C::TM_DP + hf * 64 + c * 32, vd);
-          tmem_ld_wait();
-          if (c == 1) {  // S^T / dP^T of this half are in registers: issuer A may overwrite them with tile i + 1
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sdp_free[hf]);
-            if (tri) CB_TR(tb + 3);
-          }
+          tmem_ld_32x32b_x32(lane_addr + C::TM_S + hf * 64 + c * 32, vs_all[c]);
+          tmem_ld_32x32b_x32(lane_addr + C::TM_DP + hf * 64 + c * 32, vd_all[c]);
+        }
+        tmem_ld_wait();
+        // S^T / dP^T of this half are in registers: issuer A may overwrite them with tile i + 1 right away
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdp_free[hf]);
+        if (tri) CB_TR(tb + 3);
+        if (token) {
+          if (hf == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t* vs = vs_all[c];
+          const uint32_t* vd = vd_all[c];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             float4 nl, dsv;  // explicit shared-memory loads (broadcast): a generic LD here serialises on its latency
@@ -1418,12 +1434,22 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                          : "memory");
           }
         }
+        if (token) {  // math done: pass the token (the very last pass of half 1 has no taker)
+          if (hf == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+          else if (i + 1 < n_q) asm volatile("bar.arrive 1, 256;" ::: "memory");
+        }
       } else {
 #pragma unroll
         for (int g = 0; g < 32; ++g) pk[g] = 0u, dsk[g] = 0u;
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_free[hf]);
+        if (token) {  // keep the token protocol balanced on the dead half: take it and pass it on
+          if (hf == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (hf == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+          else if (i + 1 < n_q) asm volatile("bar.arrive 1, 256;" ::: "memory");
+        }
 #pragma unroll
         for (int vcol = 0; vcol < 8; ++vcol)
           asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ds_s32 + sw128_vec_offset(r, vcol)), "r"(0u) : "memory");
@@ -1621,6 +1647,11 @@ extern "C" int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, l
   a.dk = (bf16*)dk, a.dk_sb = dk_sb, a.dk_sn = dk_sn, a.dk_sh = dk_sh;
   a.dv = (bf16*)dv, a.dv_sb = dv_sb, a.dv_sn = dv_sn, a.dv_sh = dv_sh;
   a.B = B, a.H = H, a.Nq = Nq, a.Nk = Nk, a.scale = scale, a.scale_log2 = scale * LOG2E;
+  static const int token = [] {
+    const char* e = getenv("CB_ATTN_BWD_TOKEN");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  a.token = token;
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 64)
     return launch_bwd<64>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh,

@@ -168,6 +168,36 @@ __global__ void scale_cast_kernel(const float* __restrict__ src, bf16* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// ScaleIntensity of a raw-dtype batch: 16 raw bytes per thread and step, fp32 out as 16-byte vectors
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scale_intensity_kernel(const T* __restrict__ raw, const float* __restrict__ lo, const float* __restrict__ hi,
+                                       float* __restrict__ out, long long n_per_sample) {
+  pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte load
+  const int b = blockIdx.y;
+  const float l = __ldg(lo + b), span = __ldg(hi + b) - l;
+  const float inv = span > 0.f ? 1.0f / span : 0.f;
+  const T* src = raw + (long long)b * n_per_sample;
+  float* dst = out + (long long)b * n_per_sample;
+  const long long nv = n_per_sample / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const T* e = reinterpret_cast<const T*>(&u);
+    float4* o = reinterpret_cast<float4*>(dst + i * V);
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k)
+      o[k] = make_float4((static_cast<float>(e[4 * k]) - l) * inv, (static_cast<float>(e[4 * k + 1]) - l) * inv,
+                         (static_cast<float>(e[4 * k + 2]) - l) * inv, (static_cast<float>(e[4 * k + 3]) - l) * inv);
+  }
+  if (blockIdx.x == 0) {  // ragged tail of a sample whose size is not a multiple of V
+    for (long long i = nv * V + threadIdx.x; i < n_per_sample; i += blockDim.x)
+      dst[i] = (static_cast<float>(src[i]) - l) * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // patchify / unpatchify: one thread per IMAGE element (image side is the contiguous stream)
 // ---------------------------------------------------------------------------------------
 template <typename T, bool INVERSE>
@@ -547,6 +577,27 @@ inline int blocks_for(long long work, int threads) {
 }
 
 }  // namespace
+
+extern "C" int cb_scale_intensity(const void* raw, int raw_dtype, const float* lo, const float* hi, float* out, int B,
+                                  long long n_per_sample, void* stream) {
+  if (B <= 0 || n_per_sample <= 0) return 0;
+  const int esz = raw_dtype == CB_DT_U8 ? 1 : (raw_dtype == CB_DT_F32 ? 4 : 2);
+  CB_CHECK_ARG(raw_dtype == CB_DT_U8 || raw_dtype == CB_DT_I16 || raw_dtype == CB_DT_U16 || raw_dtype == CB_DT_F32,
+               "scale_intensity: raw dtype %d not supported", raw_dtype);
+  CB_CHECK_ARG(((uintptr_t)raw & 15) == 0 && ((uintptr_t)out & 15) == 0 && (n_per_sample * esz) % 16 == 0,
+               "scale_intensity: samples must start on 16-byte boundaries");
+  const int per_sample = blocks_for(n_per_sample * esz / 16 + 1, 256);
+  dim3 grid(per_sample < 64 ? per_sample : 64, B);  // 64 x B blocks of 256 threads cover a 16-sample batch several times over
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (raw_dtype) {
+    case CB_DT_U8: cb_launch(scale_intensity_kernel<uint8_t>, grid, 256, 0, s, (const uint8_t*)raw, lo, hi, out, n_per_sample); break;
+    case CB_DT_I16: cb_launch(scale_intensity_kernel<int16_t>, grid, 256, 0, s, (const int16_t*)raw, lo, hi, out, n_per_sample); break;
+    case CB_DT_U16: cb_launch(scale_intensity_kernel<uint16_t>, grid, 256, 0, s, (const uint16_t*)raw, lo, hi, out, n_per_sample); break;
+    default: cb_launch(scale_intensity_kernel<float>, grid, 256, 0, s, (const float*)raw, lo, hi, out, n_per_sample); break;
+  }
+  CB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   if (n <= 0) return 0;

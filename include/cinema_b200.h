@@ -24,7 +24,7 @@ extern "C" {
 
 #define CINEMA_B200_ABI_VERSION 1
 
-enum { CB_DT_BF16 = 0, CB_DT_F32 = 1 };
+enum { CB_DT_BF16 = 0, CB_DT_F32 = 1, CB_DT_U8 = 2, CB_DT_I16 = 3, CB_DT_U16 = 4 };
 enum { CB_EPI_NONE = 0, CB_EPI_GELU = 1, CB_EPI_GELU_BWD = 2 };
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -144,6 +144,13 @@ int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int
                       void* stream);
 /* dst[i] = bf16(src[i] * scale * f), f = 1 (scale_dev NULL), *scale_dev (group == 0) or scale_dev[i / group] (group > 0,
  * a multiple of 4 dividing n: per-sample factors, the backward of DropPath, cinema/vit.py:606,608) */
+/* Input pipeline, device side: MONAI ScaleIntensity(minv=0, maxv=1) of a raw-dtype batch in ONE pass (the `ScaleIntensityd`
+ * of cinema/mae/pretrain.py:184 applied after the upload instead of on 16 CPU workers):
+ *   out[b, i] = (float(raw[b, i]) - lo[b]) * inv[b],  inv[b] = hi[b] > lo[b] ? 1 / (hi[b] - lo[b]) : 0   (fp32)
+ * raw: B samples of n_per_sample elements of raw_dtype (CB_DT_U8 / CB_DT_I16 / CB_DT_U16 / CB_DT_F32), contiguous;
+ * lo / hi: fp32 [B] per-sample minimum / maximum (the shard index carries them); a constant sample maps to 0. */
+int cb_scale_intensity(const void* raw, int raw_dtype, const float* lo, const float* hi, float* out, int B,
+                       long long n_per_sample, void* stream);
 int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale, long long group,
                        void* stream);
 

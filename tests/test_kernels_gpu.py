@@ -589,3 +589,28 @@ def test_scale_cast_grouped():
     assert torch.equal(dst, (src * 1.5).to(torch.bfloat16))
     with pytest.raises((RuntimeError, AssertionError)):
         _C.scale_cast(src, dst, s[:4].contiguous(), group=6)  # group must be a multiple of 4 dividing n
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int16, torch.uint16, torch.float32])
+def test_scale_intensity_kernel(dtype):
+    """cb_scale_intensity == MONAI ScaleIntensity(0, 1) per sample ((x - min) / (max - min), constant sample -> 0),
+    bit-exact against the same fp32 arithmetic in torch (cinema/mae/pretrain.py:184)."""
+    from cinema_b200.data import scale_intensity
+
+    g = torch.Generator().manual_seed(0)
+    b, shape = 5, (1, 24, 20, 6)
+    if dtype == torch.float32:
+        raw = torch.rand(b, *shape, generator=g) * 3000 - 1000
+    elif dtype == torch.uint16:
+        raw = torch.randint(0, 60000, (b, *shape), generator=g, dtype=torch.int32).to(torch.uint16)
+    else:
+        lim = 255 if dtype == torch.uint8 else 3000
+        raw = torch.randint(0 if dtype == torch.uint8 else -500, lim, (b, *shape), generator=g, dtype=torch.int32).to(dtype)
+    raw[2] = 7  # constant sample
+    flat = raw.reshape(b, -1).to(torch.float32)
+    lo, hi = flat.min(1).values.contiguous(), flat.max(1).values.contiguous()
+    out = torch.empty(raw.shape, device=DEV, dtype=torch.float32)
+    _C.scale_intensity(raw.to(DEV), lo.to(DEV), hi.to(DEV), out)
+    ref = scale_intensity(raw.to(torch.float32) if dtype == torch.uint16 else raw, lo, hi)
+    assert torch.equal(out.cpu(), ref)
+    assert float(out[2].abs().max()) == 0.0 and float(out.max()) == 1.0 and float(out.min()) == 0.0
