@@ -44,7 +44,8 @@ _SIGNATURES = {
                          + [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "cb_attention_bwd": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong] * 5 + [c_void_p]
                          + [c_void_p, c_longlong, c_longlong, c_longlong] * 3
-                         + [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+                         + [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
     "cb_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_longlong,
                                  c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_void_p]),
     "cb_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
@@ -246,14 +247,19 @@ def attention_bwd_workspace(b: int, h: int, nq: int, d: int, device) -> tuple[to
             torch.empty((b, h, nq, d), dtype=torch.float32, device=device))
 
 
-def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale: float) -> None:
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale: float, dq_colsum=None, dk_colsum=None,
+                  dv_colsum=None) -> None:
+    """``d?_colsum`` (fp32 (H * d,), optional): += column sums of the stored bf16 dQ / dK / dV (projection bias gradients)."""
     b, nq, h, d = q.shape
     nk = k.shape[1]
+    for cs in (dq_colsum, dk_colsum, dv_colsum):
+        assert cs is None or (cs.dtype == torch.float32 and cs.numel() == h * d and cs.is_contiguous())
     assert delta.dtype == torch.float32 and delta.numel() >= 2 * b * h * ((nq + 127) // 128 * 128), "delta workspace too small"
     assert dq_acc.dtype == torch.float32 and dq_acc.numel() >= b * h * nq * d
     _check(lib().cb_attention_bwd(*_bnh(q, "q"), *_bnh(k, "k"), *_bnh(v, "v"), *_bnh(o, "o"), *_bnh(do, "do"),
                                   _ptr(lse), *_bnh(dq, "dq"), *_bnh(dk, "dk"), *_bnh(dv, "dv"), _ptr(delta),
-                                  _ptr(dq_acc), b, h, nq, nk, d, float(scale), _stream()), "attention_bwd")
+                                  _ptr(dq_acc), b, h, nq, nk, d, float(scale), _ptr(dq_colsum), _ptr(dk_colsum),
+                                  _ptr(dv_colsum), _stream()), "attention_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None, act: bool = False) -> None:

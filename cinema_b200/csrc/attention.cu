@@ -751,6 +751,8 @@ struct AttnBwdArgs {
   int B, H, Nq, Nk;
   float scale, scale_log2;
   int token;  // second-generation kernel: alternate the exp2 section between the two compute warpgroups
+  float* dk_cs;  // optional [H * D] fp32: += column sums of the stored bf16 dK / dV (k / v projection bias gradients)
+  float* dv_cs;
 };
 
 template <int D>
@@ -1496,6 +1498,26 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         reinterpret_cast<uint4*>(dv_ptr + c * 16)[0] = x0;
         reinterpret_cast<uint4*>(dv_ptr + c * 16)[1] = x1;
       }
+      if (p.dk_cs != nullptr || p.dv_cs != nullptr) {
+        // bias gradients of the k / v projections: column sums of the ROUNDED values just stored, over this warp's 32
+        // key rows (shuffle tree), one fp32 atomic per column and warp
+        const bool ok = kv_row < p.Nk;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float sk = ok ? bf16_round(__uint_as_float(a[j])) : 0.f;
+          float sv = ok ? bf16_round(__uint_as_float(v[j])) : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sk += __shfl_xor_sync(0xffffffffu, sk, o);
+            sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          }
+          if (lane == j) {  // spread the 16 atomics of a chunk over 16 lanes
+            const int col = h * D + hf * (D / 2) + c * 16 + j;
+            if (p.dk_cs != nullptr) atomicAdd(p.dk_cs + col, sk);
+            if (p.dv_cs != nullptr) atomicAdd(p.dv_cs + col, sv);
+          }
+        }
+      }
     }
     if (warp == 0) CB_TR(1003);
   }
@@ -1552,30 +1574,48 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_sb, lo
   }
 }
 
-// dq[b,q,h,:] = bf16(dq_acc[b,h,q,:])
+// dq[b,q,h,:] = bf16(dq_acc[b,h,q,:]); optionally colsum[h * D + c] += sum over (b, q) of the rounded values (the q
+// projection's bias gradient).  Block = one (b, h) and a strided set of its query rows; D / 8 threads per row.
 template <int D>
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long sb, long long sn,
-                                       long long sh, int B, int H, int Nq) {
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long sb, long long sn, long long sh, int B,
+                       int H, int Nq, float* __restrict__ colsum) {
   pdl_prologue();  // PDL: release the next launch, then wait for the previous kernel's results
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  constexpr int VPR = D / 8;  // 16-byte output vectors per row
-  const long long row = gid / VPR;
-  const int vcol = (int)(gid % VPR);
-  if (row >= (long long)B * H * Nq) return;
-  const int q = (int)(row % Nq);
-  const int h = (int)((row / Nq) % H);
-  const int b = (int)(row / ((long long)Nq * H));
-  const float4 x = __ldg(reinterpret_cast<const float4*>(acc + row * D + vcol * 8));
-  const float4 y = __ldg(reinterpret_cast<const float4*>(acc + row * D + vcol * 8 + 4));
-  *reinterpret_cast<uint4*>(dq + b * sb + (long long)q * sn + (long long)h * sh + vcol * 8) =
-      make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  constexpr int VPR = D / 8;       // 16-byte output vectors per row
+  constexpr int RPB = 256 / VPR;   // rows per block pass
+  const int vcol = threadIdx.x % VPR, rsub = threadIdx.x / VPR;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const float* a = acc + ((long long)b * H + h) * Nq * D;
+  bf16* out = dq + b * sb + (long long)h * sh + vcol * 8;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int q = blockIdx.x * RPB + rsub; q < Nq; q += gridDim.x * RPB) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a + (long long)q * D + vcol * 8));
+    const float4 y = __ldg(reinterpret_cast<const float4*>(a + (long long)q * D + vcol * 8 + 4));
+    const uint4 pk = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    *reinterpret_cast<uint4*>(out + (long long)q * sn) = pk;
+    if (colsum != nullptr) {
+      const float2 p0 = unpack_bf16(pk.x), p1 = unpack_bf16(pk.y), p2 = unpack_bf16(pk.z), p3 = unpack_bf16(pk.w);
+      cs[0] += p0.x, cs[1] += p0.y, cs[2] += p1.x, cs[3] += p1.y, cs[4] += p2.x, cs[5] += p2.y, cs[6] += p3.x, cs[7] += p3.y;
+    }
+  }
+  if (colsum == nullptr) return;
+  __shared__ float red[256][9];  // (+1: conflict-free column reads)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = cs[j];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    const int vc = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int r = 0; r < RPB; ++r) t += red[r * VPR + vc][j];
+    atomicAdd(colsum + h * D + threadIdx.x, t);
+  }
 }
 
 template <int D>
 int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                const AttnBwdArgs& a, const bf16* o, long long o_sb, long long o_sn, long long o_sh, const bf16* d_o,
                long long do_sb, long long do_sn, long long do_sh, const float* lse, bf16* dq, long long dq_sb,
-               long long dq_sn, long long dq_sh, cudaStream_t stream) {
+               long long dq_sn, long long dq_sh, float* dq_cs, cudaStream_t stream) {
   using C = BwdCfg<D>;
   const long long rows = (long long)a.B * a.H * a.Nq;
   const long long rows_p = (long long)a.B * a.H * a.NqP;
@@ -1616,9 +1656,12 @@ int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& 
     cb_launch(kern, grid, BWD2_THREADS, C2::SMEM_BYTES, stream, tq, tk, tv, tdo, tdq, a);
   }
   CB_LAUNCH_CHECK();
-  const long long vecs = rows * (D / 8);
-  cb_launch(attn_dq_convert_kernel<D>, (unsigned)((vecs + 255) / 256), 256, 0, stream, a.dq_acc, dq, dq_sb, dq_sn, dq_sh, a.B,
-                                                                                a.H, a.Nq);
+  {
+    constexpr int RPB = 256 / (D / 8);
+    const int xb = (a.Nq + 4 * RPB - 1) / (4 * RPB);  // ~4 row passes per block
+    cb_launch(attn_dq_convert_kernel<D>, dim3(xb < 1 ? 1 : xb, a.H, a.B), 256, 0, stream, a.dq_acc, dq, dq_sb, dq_sn, dq_sh,
+              a.B, a.H, a.Nq, dq_cs);
+  }
   CB_LAUNCH_CHECK();
   return 0;
 }
@@ -1632,7 +1675,8 @@ extern "C" int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, l
                                 const float* lse, void* dq, long long dq_sb, long long dq_sn, long long dq_sh, void* dk,
                                 long long dk_sb, long long dk_sn, long long dk_sh, void* dv, long long dv_sb,
                                 long long dv_sn, long long dv_sh, float* delta, float* dq_acc, int B, int H, int Nq,
-                                int Nk, int head_dim, float scale, void* stream) {
+                                int Nk, int head_dim, float scale, float* dq_colsum, float* dk_colsum, float* dv_colsum,
+                                void* stream) {
   CB_CHECK_ARG(head_dim == 32 || head_dim == 64, "attention_bwd: head_dim %d not supported (32 or 64)", head_dim);
   CB_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && Nk > 0, "attention_bwd: empty problem");
   CB_CHECK_ARG(delta != nullptr && dq_acc != nullptr, "attention_bwd: workspaces missing");
@@ -1652,10 +1696,16 @@ extern "C" int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, l
     return e != nullptr ? atoi(e) : 1;
   }();
   a.token = token;
+  a.dk_cs = dk_colsum, a.dv_cs = dv_colsum;
+  {
+    const char* e = getenv("CB_ATTN_BWD");
+    CB_CHECK_ARG((dk_colsum == nullptr && dv_colsum == nullptr) || e == nullptr || atoi(e) != 1,
+                 "attention_bwd: the first-generation kernel (CB_ATTN_BWD=1) has no fused dK / dV column sums");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 64)
     return launch_bwd<64>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh,
-                          lse, (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
+                          lse, (bf16*)dq, dq_sb, dq_sn, dq_sh, dq_colsum, s);
   return launch_bwd<32>(tq, tk, tv, tdo, a, (const bf16*)o, o_sb, o_sn, o_sh, (const bf16*)d_o, do_sb, do_sn, do_sh, lse,
-                        (bf16*)dq, dq_sb, dq_sn, dq_sh, s);
+                        (bf16*)dq, dq_sb, dq_sn, dq_sh, dq_colsum, s);
 }

@@ -198,13 +198,14 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, scale: float) -> None:
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, scale: float, dq_colsum=None, dk_colsum=None, dv_colsum=None) -> None:
+    """``d?_colsum``: bias-gradient buffers of the q / k / v projections (fp32 (H * d,)), accumulated by the kernel."""
     b, nq, h, d = q.shape
     if k.shape[1] == 0:  # no keys: the output did not depend on q (and there is no k / v to differentiate)
         dq.zero_()
         return
     delta, dq_acc = _C.attention_bwd_workspace(b, h, nq, d, q.device)
-    _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale)
+    _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale, dq_colsum, dk_colsum, dv_colsum)
 
 
 # ------------------------------------------------------------------------------------------
@@ -342,9 +343,11 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
         q5 = qsave.view(b, n, 3, w.n_heads, hd)
         dqkv = torch.empty_like(qsave)
         d5 = dqkv.view(b, n, 3, w.n_heads, hd)
-        attn_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o, do, lse, d5[:, :, 0], d5[:, :, 1], d5[:, :, 2], w.scale)
+        gb = w.qkv.gb if w.qkv is not None else None  # fused [q | k | v] bias gradient: summed inside the attention backward
+        attn_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o, do, lse, d5[:, :, 0], d5[:, :, 1], d5[:, :, 2], w.scale,
+                 *((gb[:d], gb[d:2 * d], gb[2 * d:]) if gb is not None else (None, None, None)))
         if w.qkv is not None:
-            dh1 = linear_bwd(dqkv, h1, w.qkv)
+            dh1 = linear_bwd(dqkv, h1, w.qkv, bias_done=gb is not None)
         else:
             # separate q / kv weights: two dgrads summed through the fp32 accumulate path
             tmp = torch.zeros((m, d), dtype=F32, device=x.device)
@@ -358,8 +361,8 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
     else:
         q = qsave.view(b, n, w.n_heads, hd)
         dq2 = torch.empty_like(qsave)
-        attn_bwd(q, kv[0], kv[1], o, do, lse, dq2.view(b, n, w.n_heads, hd), dkv[0], dkv[1], w.scale)
-        dh1 = linear_bwd(dq2, h1, w.q)
+        attn_bwd(q, kv[0], kv[1], o, do, lse, dq2.view(b, n, w.n_heads, hd), dkv[0], dkv[1], w.scale, dq_colsum=w.q.gb)
+        dh1 = linear_bwd(dq2, h1, w.q, bias_done=w.q.gb is not None)
     dx32, dx16 = ln_bwd(dh1, x, mean1, rstd1, w.norm1, dres=dx32, dx32=dx32, dxsum=out_bias)
     return dx32, dx16
 

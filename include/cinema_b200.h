@@ -91,7 +91,11 @@ int cb_attention_bwd(const void* q, long long q_sb, long long q_sn, long long q_
                      long long do_sn, long long do_sh, const float* lse, void* dq, long long dq_sb, long long dq_sn,
                      long long dq_sh, void* dk, long long dk_sb, long long dk_sn, long long dk_sh, void* dv,
                      long long dv_sb, long long dv_sn, long long dv_sh, float* delta, float* dq_acc, int B, int H,
-                     int Nq, int Nk, int head_dim, float scale, void* stream);
+                     int Nq, int Nk, int head_dim, float scale, float* dq_colsum, float* dk_colsum, float* dv_colsum,
+                     void* stream);
+/* dq_colsum / dk_colsum / dv_colsum (fp32 [H * head_dim] each, any may be NULL): += column sums over (batch, token) of the
+ * bf16 values stored to dQ / dK / dV -- the bias gradients of the q / k / v projections (qkv_bias=True,
+ * cinema/vit.py:472-473), fused into the dQ conversion pass and the dK / dV epilogue instead of three more passes. */
 
 /* ---- LayerNorm (row-wise over the last dim, fp32 statistics) -------------------------- *
  * y = (x - mean) * rstd * gamma + beta.  x fp32 [M,D] (row pitch ldx).  y16 (bf16) and/or y32

@@ -93,7 +93,7 @@ def attention_fwd(q, k, v, o, lse, scale):
     lse.view(b, h, nq).copy_(l)
 
 
-def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale):
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale, dq_colsum=None, dk_colsum=None, dv_colsum=None):
     b, nq, h, d = q.shape
     s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
     p = torch.exp(s - lse.view(b, h, nq)[..., None])
@@ -103,6 +103,9 @@ def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale):
     dv.copy_(torch.einsum("bhqk,bqhd->bkhd", p.to(BF16).float(), do.float()).to(BF16))
     dk.copy_(torch.einsum("bhqk,bqhd->bkhd", ds, q.float()).to(BF16))
     dq.copy_(torch.einsum("bhqk,bkhd->bqhd", ds, k.float()).to(BF16))
+    for cs, t in ((dq_colsum, dq), (dk_colsum, dk), (dv_colsum, dv)):
+        if cs is not None:
+            cs += t.float().sum((0, 1)).reshape(-1)
 
 
 def layernorm_fwd(x, gamma, beta, eps, y16=None, y32=None, mean=None, rstd=None, act=False):

@@ -97,3 +97,28 @@ def test_attention_backward(b, h, nq, nk, d, fused):
     assert rel_err(dq, qr.grad) < 6e-3
     assert rel_err(dkv[:, :, 0], kr.grad) < 6e-3
     assert rel_err(dkv[:, :, 1], vr.grad) < 6e-3
+
+
+@pytest.mark.parametrize("b,h,nq,nk,d", [(2, 12, 685, 685, 64), (2, 16, 517, 300, 32), (1, 2, 130, 70, 64), (3, 4, 64, 129, 32)])
+def test_attention_backward_fused_bias_column_sums(b, h, nq, nk, d):
+    """dq / dk / dv column sums (the q / k / v projection bias gradients, cinema/vit.py:472-473) accumulated by the
+    backward itself: equal to a separate column sum over the stored bf16 gradients, added on top of what the buffers held."""
+    q, k, v = make_qkv(b, h, nq, nk, d, seed=3 + nq, fused=False)
+    scale = d ** -0.5
+    o = torch.empty(b, nq, h, d, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(b, h, nq, device=DEV)
+    _C.attention_fwd(q, k, v, o, lse, scale)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    do = torch.randn(b, nq, h, d, device=DEV, generator=g).to(torch.bfloat16)
+    dq, dk, dv = torch.empty_like(q), torch.empty(b, nk, h, d, device=DEV, dtype=torch.bfloat16), torch.empty(b, nk, h, d, device=DEV, dtype=torch.bfloat16)
+    delta, dq_acc = _C.attention_bwd_workspace(b, h, nq, d, DEV)
+    base = [torch.randn(h * d, device=DEV, generator=g) for _ in range(3)]
+    cs = [t.clone() for t in base]
+    _C.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, delta, dq_acc, scale, cs[0], cs[1], cs[2])
+    dq2, dk2, dv2 = torch.empty_like(dq), torch.empty_like(dk), torch.empty_like(dv)
+    _C.attention_bwd(q, k, v, o, do, lse, dq2, dk2, dv2, delta, dq_acc, scale)
+    assert torch.equal(dk, dk2) and torch.equal(dv, dv2)  # the side outputs do not change the main ones
+    assert rel_err(dq, dq2.float()) < 1e-3                # (dQ: fp32 atomics reorder the sums between runs)
+    for got, b0, t in zip(cs, base, (dq, dk, dv)):
+        want = b0.double() + t.double().sum((0, 1)).reshape(-1)
+        torch.testing.assert_close(got.double(), want, rtol=1e-4, atol=1e-3 * float(t.float().abs().max()) * (b * t.shape[1]) ** 0.5 + 1e-4)
