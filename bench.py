@@ -209,8 +209,10 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
                 a_, b_ = args[0], args[1]
                 m_, k_ = (a_.shape[1], a_.shape[0]) if kwargs.get("a_mn") else (a_.shape[0], a_.shape[1])
                 n_ = b_.shape[1] if kwargs.get("b_mn") else b_.shape[0]
+                o_ = args[2]
                 shapes.append((f"M{m_} N{n_} K{k_} a_mn={int(bool(kwargs.get('a_mn')))} b_mn={int(bool(kwargs.get('b_mn')))} "
-                               f"epi={kwargs.get('epilogue', 0)} res={int(kwargs.get('residual') is not None)}", s, e,
+                               f"epi={kwargs.get('epilogue', 0)} res={int(kwargs.get('residual') is not None)} "
+                               f"o32={int(o_ is not None and o_.dtype == torch.float32)} acc={int(bool(kwargs.get('accumulate')))}", s, e,
                                2.0 * m_ * n_ * k_))
             records.append((tag, flops_of(name, args, kwargs), s, e))
             if name in ("gemm", "attention_fwd", "attention_bwd"):
@@ -287,7 +289,25 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
     for name, v in rep.items():  # tensor-core kernels: take the replayed (queue-fed) device times
         agg[name] = v
     own = sum(a[0] for a in agg.values())
-    top_shapes = [{"gemm": k, "launches": v[2], "ms": round(v[0], 3), "tflops": round(v[1] / v[0] / 1e9, 1)}
+    peaks, _ = measured_peaks()
+
+    def shape_roof(tag: str, ms: float, launches: int, flops: float) -> dict:
+        """Which roof bounds this GEMM shape?  Algorithmic bytes: A + B (bf16) + the stored output (+ the fp32 residual it
+        reads, + the bf16 GELU' operand, + the second bf16 output of the GELU flavour); split-K accumulation reads and
+        writes the fp32 output."""
+        f = dict(kv.split("=") for kv in tag.split()[3:])
+        m, n, k = (int(x[1:]) for x in tag.split()[:3])
+        o32, res, epi, acc = int(f["o32"]), int(f["res"]), int(f["epi"]), int(f["acc"])
+        by = 2.0 * (m * k + n * k) + m * n * (4 if o32 else 2) * (2 if acc else 1) + res * 4.0 * m * n
+        by += 2.0 * m * n if epi in (1, 2) else 0.0
+        t_hbm = by / (peaks["hbm_gbs"] * 1e9)
+        t_tc = (flops / launches) / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 1e12)
+        t = ms / launches / 1e3
+        bound = "hbm" if t_hbm > t_tc else "tensor"
+        return {"bound": bound, "frac_of_bound": round(max(t_hbm, t_tc) / t, 3), "gb_per_s": round(by / t / 1e9, 0)}
+
+    top_shapes = [{"gemm": k, "launches": v[2], "ms": round(v[0], 3), "tflops": round(v[1] / v[0] / 1e9, 1),
+                   **shape_roof(k, v[0], v[2], v[1])}
                   for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:24]]
     return {"step_ms": total, "own_kernels_ms": own, "torch_and_gaps_ms": total - own,
             "note": "one eager step on a single stream, CUDA events per C-ABI launch; GEMM / attention launches re-timed by "
