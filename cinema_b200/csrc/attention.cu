@@ -1188,7 +1188,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tma_load_4d(smem + C::OFF_V, &tm_v, kv_full, 0, h, kv0, b);
         for (int i = 0; i < n_q; ++i) {
           const int s = i % C::STAGES;
-          mbar_wait(&qdo_empty[s], ((i / C::STAGES) & 1) ^ 1);
+          if (i >= C::STAGES) mbar_wait(&qdo_empty[s], ((i / C::STAGES) & 1) ^ 1);  // (the first fills find the ring empty)
           mbar_expect_tx(&qdo_full[s], 2 * C::TILE_BYTES + 1024);
           tma_load_4d(smem + C::OFF_Q + s * C::TILE_BYTES, &tm_q, &qdo_full[s], 0, h, i * 128, b);
           tma_load_4d(smem + C::OFF_DO + s * C::TILE_BYTES, &tm_do, &qdo_full[s], 0, h, i * 128, b);

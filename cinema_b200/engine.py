@@ -343,9 +343,15 @@ def block_bwd(dx32: torch.Tensor, dx16: torch.Tensor, w: BlockW, b: int, saved,
         q5 = qsave.view(b, n, 3, w.n_heads, hd)
         dqkv = torch.empty_like(qsave)
         d5 = dqkv.view(b, n, 3, w.n_heads, hd)
-        gb = w.qkv.gb if w.qkv is not None else None  # fused [q | k | v] bias gradient: summed inside the attention backward
+        # fused [q | k | v] bias gradient: the q part is summed inside the attention backward (its dQ conversion pass, free),
+        # the k | v part by one column-sum pass over dqkv[:, d:].  The kernel can also sum dK / dV in its epilogue
+        # (dk_colsum / dv_colsum), but at 685 x 685 x 12 heads that puts 590 k single-lane atomics on 48 cache lines:
+        # 193 us against 152 + 12 us for the separate pass (tools/ab_attn_colsum.py, profiles/r02_attention.md)
+        gb = w.qkv.gb if w.qkv is not None else None
         attn_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o, do, lse, d5[:, :, 0], d5[:, :, 1], d5[:, :, 2], w.scale,
-                 *((gb[:d], gb[d:2 * d], gb[2 * d:]) if gb is not None else (None, None, None)))
+                 dq_colsum=gb[:d] if gb is not None else None)
+        if gb is not None:
+            _C.colsum(dqkv[:, d:], gb[d:])
         if w.qkv is not None:
             dh1 = linear_bwd(dqkv, h1, w.qkv, bias_done=gb is not None)
         else:

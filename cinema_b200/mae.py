@@ -47,10 +47,11 @@ def get_batch_random_patch_mask(batch_size: int, n_patches: int, mask_ratio: flo
     n_keep = int(n_patches * (1 - mask_ratio))
     noise = torch.rand(batch_size, n_patches, device=device)
     ids_shuffle = torch.argsort(noise, dim=1)
-    ids_restore = torch.argsort(ids_shuffle, dim=1)
+    # the reference sorts a second time (ids_restore = argsort(ids_shuffle)) and gathers a [0..0 1..1] row through it;
+    # the argsort of a permutation is its inverse, so that is exactly "clear the n_keep first entries of ids_shuffle":
+    # one scatter instead of a second radix sort + gather, bit-identical masks
     mask = torch.ones((batch_size, n_patches), dtype=torch.bool, device=device)
-    mask[:, :n_keep] = False
-    return torch.gather(mask, dim=1, index=ids_restore)
+    return mask.scatter_(1, ids_shuffle[:, :n_keep], False)
 
 
 def get_decoder_patch_size(image_size, n_conv_layers, enc_patch_size, enc_scale_factor) -> tuple[int, ...]:
