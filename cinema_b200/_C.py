@@ -34,6 +34,8 @@ _SIGNATURES = {
     "cb_set_pdl": (c_int, [c_int]),
     "cb_attention_trace": (c_int, [c_void_p]),
     "cb_scale_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
+    "cb_zoom_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                  c_void_p]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -384,6 +386,27 @@ def scale_intensity(raw: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, out: 
     assert lo.numel() == b and hi.numel() == b and lo.is_contiguous() and hi.is_contiguous()
     _check(lib().cb_scale_intensity(_ptr(raw), _RAW_DT[raw.dtype], _ptr(lo), _ptr(hi), _ptr(out), b, raw.numel() // b,
                                     _stream()), "scale_intensity")
+    return out
+
+
+def zoom_intensity(raw: torch.Tensor, extent: torch.Tensor, zoom: torch.Tensor, out: torch.Tensor,
+                   keys_ws: torch.Tensor | None = None) -> torch.Tensor:
+    """RandZoom(keep_size) -> ScaleIntensity -> SpatialPad("end") of a raw-dtype batch on the device (cb_zoom_intensity).
+    raw (B, 1, *size): frames stored in the model's input size, each occupying the corner [0, extent[b]) of it; extent
+    (B, 3) int32 (unused axes 1); zoom (B,) fp32, 1 = identity; 3 spatial axes -> trilinear, 2 -> bicubic.  Returns
+    ``out`` (B, 1, *size) fp32 in [0, 1], zero outside the frame."""
+    assert raw.dtype in _RAW_DT and raw.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    assert out.shape == raw.shape and raw.dim() in (4, 5) and raw.shape[1] == 1
+    b = raw.shape[0]
+    size = tuple(raw.shape[2:])
+    assert extent.dtype == torch.int32 and extent.is_contiguous() and tuple(extent.shape) == (b, 3)
+    assert zoom.dtype == torch.float32 and zoom.is_contiguous() and zoom.numel() == b
+    if keys_ws is None:
+        keys_ws = torch.empty(2 * b, dtype=torch.int32, device=raw.device)
+    assert keys_ws.numel() >= 2 * b and keys_ws.element_size() == 4 and keys_ws.is_contiguous()
+    sz = (c_int * len(size))(*size)
+    _check(lib().cb_zoom_intensity(_ptr(raw), _RAW_DT[raw.dtype], _ptr(extent), _ptr(zoom), _ptr(out), _ptr(keys_ws), b,
+                                   len(size), sz, int(len(size) == 2), _stream()), "zoom_intensity")
     return out
 
 

@@ -570,6 +570,156 @@ inline int tok_grid(int T) {
   return want < cap ? want : cap;
 }
 
+// ---------------------------------------------------------------------------------------
+// RandZoom(keep_size) + ScaleIntensity + SpatialPad("end") of a raw-dtype batch on the device (cinema/mae/pretrain.py:
+// 163-199): the zoom is MONAI's `Zoom` = torch `interpolate(scale_factor = z, align_corners = False)` of the UNPADDED frame
+// (trilinear for SAX, bicubic with A = -0.75 for LAX) centre-padded with zeros / centre-cropped back to the frame's own
+// size; ScaleIntensity then takes min / max over that zoomed frame, and the model-size padding is zero after scaling.
+// Pass 1 resamples into fp32 and reduces the per-sample min / max (monotone uint keys, atomicMin / atomicMax); pass 2
+// scales in place.  z == 1 reproduces the input exactly (all interpolation weights are 0 / 1).
+// ---------------------------------------------------------------------------------------
+struct ZoomGeom {
+  int nd;    // 2 (bicubic) or 3 (trilinear)
+  int S[3];  // model input size per axis (row-major, S[2] = 1 when nd == 2): the stride space of raw and out
+};
+
+__device__ __forceinline__ unsigned f32_order_key(float v) {  // monotone float -> uint
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_key(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct ZoomAxis {
+  int E, O, half;
+  bool crop;
+};
+__device__ __forceinline__ ZoomAxis zoom_axis(int extent, float z) {
+  ZoomAxis a;
+  a.E = extent;
+  a.O = (int)floor((double)extent * (double)z);  // torch: output size = floor(input size * scale_factor), in double
+  const int diff = a.E - a.O;
+  a.crop = diff < 0;
+  a.half = (diff < 0 ? -diff : diff) / 2;  // MONAI Zoom keep_size: pad [half, diff - half] or slice [half, half + E)
+  return a;
+}
+
+__device__ __forceinline__ float cubic_w1(float x) { return ((-0.75f + 2.f) * x - (-0.75f + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic_w2(float x) { return ((-0.75f * x + 3.75f) * x - 6.f) * x + 3.f; }
+
+template <typename T, bool CUBIC>
+__global__ void __launch_bounds__(256)
+zoom_resample_kernel(const T* __restrict__ raw, const int* __restrict__ extent, const float* __restrict__ zoom,
+                     float* __restrict__ out, unsigned* __restrict__ keys, ZoomGeom g, int B) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const long long n = (long long)g.S[0] * g.S[1] * g.S[2];
+  const T* src = raw + (long long)b * n;
+  float* dst = out + (long long)b * n;
+  const float z = __ldg(zoom + b);
+  const float rs = (float)(1.0 / (double)z);  // area_pixel_compute_scale with a given scale factor
+  ZoomAxis ax[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) ax[a] = zoom_axis(a < g.nd ? __ldg(extent + b * 3 + a) : 1, a < g.nd ? z : 1.f);
+  float vmin = INFINITY, vmax = -INFINITY;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int c[3];
+    long long r = i;
+    c[2] = (int)(r % g.S[2]), r /= g.S[2];
+    c[1] = (int)(r % g.S[1]);
+    c[0] = (int)(r / g.S[1]);
+    float v = 0.f;
+    if (c[0] < ax[0].E && c[1] < ax[1].E && c[2] < ax[2].E) {  // inside the frame (the rest is SpatialPad: 0 after scaling)
+      bool ok = true;
+      float real[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int o = ax[a].crop ? c[a] + ax[a].half : c[a] - ax[a].half;  // coordinate in the zoomed (O-sized) image
+        ok = ok && o >= 0 && o < ax[a].O;
+        real[a] = a < g.nd ? rs * ((float)o + 0.5f) - 0.5f : 0.f;
+      }
+      if (ok) {
+        if constexpr (!CUBIC) {
+          int i0[3], i1[3];
+          float l1[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float x = fmaxf(real[a], 0.f);
+            i0[a] = min((int)x, ax[a].E - 1);
+            i1[a] = i0[a] + (i0[a] < ax[a].E - 1 ? 1 : 0);
+            l1[a] = fminf(fmaxf(x - (float)i0[a], 0.f), 1.f);
+          }
+          auto at = [&](int p, int q, int s) { return static_cast<float>(src[((long long)p * g.S[1] + q) * g.S[2] + s]); };
+          const float w0 = 1.f - l1[2], w1 = l1[2];
+          const float a00 = w0 * at(i0[0], i0[1], i0[2]) + w1 * at(i0[0], i0[1], i1[2]);
+          const float a01 = w0 * at(i0[0], i1[1], i0[2]) + w1 * at(i0[0], i1[1], i1[2]);
+          const float a10 = w0 * at(i1[0], i0[1], i0[2]) + w1 * at(i1[0], i0[1], i1[2]);
+          const float a11 = w0 * at(i1[0], i1[1], i0[2]) + w1 * at(i1[0], i1[1], i1[2]);
+          v = (1.f - l1[0]) * ((1.f - l1[1]) * a00 + l1[1] * a01) + l1[0] * ((1.f - l1[1]) * a10 + l1[1] * a11);
+        } else {
+          const float fy = floorf(real[0]), fx = floorf(real[1]);
+          const int iy = (int)fy, ix = (int)fx;
+          const float ty = real[0] - fy, tx = real[1] - fx;
+          const float wy[4] = {cubic_w2(ty + 1.f), cubic_w1(ty), cubic_w1(1.f - ty), cubic_w2(2.f - ty)};
+          const float wx[4] = {cubic_w2(tx + 1.f), cubic_w1(tx), cubic_w1(1.f - tx), cubic_w2(2.f - tx)};
+          v = 0.f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int yy = min(max(iy - 1 + p, 0), ax[0].E - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int xx = min(max(ix - 1 + q, 0), ax[1].E - 1);
+              row += wx[q] * static_cast<float>(src[(long long)yy * g.S[1] + xx]);
+            }
+            v += wy[p] * row;
+          }
+        }
+      }
+      vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+    }
+    dst[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  __shared__ float smin[8], smax[8];
+  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = vmin, smax[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) vmin = fminf(vmin, smin[w]), vmax = fmaxf(vmax, smax[w]);
+    if (vmin <= vmax) {  // (a block that saw no voxel of the frame contributes nothing)
+      atomicMin(keys + b, f32_order_key(vmin));
+      atomicMax(keys + B + b, f32_order_key(vmax));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zoom_scale_kernel(float* __restrict__ out, const int* __restrict__ extent, const unsigned* __restrict__ keys, ZoomGeom g, int B) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const long long n = (long long)g.S[0] * g.S[1] * g.S[2];
+  float* dst = out + (long long)b * n;
+  const float lo = f32_from_key(keys[b]), span = f32_from_key(keys[B + b]) - lo;
+  const float inv = span > 0.f ? 1.0f / span : 0.f;
+  int E[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) E[a] = a < g.nd ? __ldg(extent + b * 3 + a) : 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long r = i;
+    const int c2 = (int)(r % g.S[2]);
+    r /= g.S[2];
+    const int c1 = (int)(r % g.S[1]), c0 = (int)(r / g.S[1]);
+    if (c0 < E[0] && c1 < E[1] && c2 < E[2]) dst[i] = (dst[i] - lo) * inv;
+  }
+}
+
 inline int blocks_for(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = (long long)cb_sm_count() * 16;
@@ -595,6 +745,45 @@ extern "C" int cb_scale_intensity(const void* raw, int raw_dtype, const float* l
     case CB_DT_U16: cb_launch(scale_intensity_kernel<uint16_t>, grid, 256, 0, s, (const uint16_t*)raw, lo, hi, out, n_per_sample); break;
     default: cb_launch(scale_intensity_kernel<float>, grid, 256, 0, s, (const float*)raw, lo, hi, out, n_per_sample); break;
   }
+  CB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cb_zoom_intensity(const void* raw, int raw_dtype, const int* extent, const float* zoom, float* out,
+                                 void* keys_ws, int B, int nd, const int* size, int cubic, void* stream) {
+  if (B <= 0) return 0;
+  CB_CHECK_ARG(raw_dtype == CB_DT_U8 || raw_dtype == CB_DT_I16 || raw_dtype == CB_DT_U16 || raw_dtype == CB_DT_F32,
+               "zoom_intensity: raw dtype %d not supported", raw_dtype);
+  CB_CHECK_ARG((nd == 2 && cubic) || (nd == 3 && !cubic), "zoom_intensity: bicubic is 2-D, trilinear is 3-D (nd=%d cubic=%d)", nd, cubic);
+  CB_CHECK_ARG(extent != nullptr && zoom != nullptr && keys_ws != nullptr && size != nullptr, "zoom_intensity: null argument");
+  ZoomGeom g;
+  g.nd = nd;
+  for (int a = 0; a < 3; ++a) g.S[a] = a < nd ? size[a] : 1;
+  CB_CHECK_ARG(g.S[0] > 0 && g.S[1] > 0 && g.S[2] > 0, "zoom_intensity: bad size");
+  const long long n = (long long)g.S[0] * g.S[1] * g.S[2];
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned* keys = reinterpret_cast<unsigned*>(keys_ws);
+  CB_CUDA(cudaMemsetAsync(keys, 0xff, sizeof(unsigned) * B, s));      // running minima
+  CB_CUDA(cudaMemsetAsync(keys + B, 0x00, sizeof(unsigned) * B, s));  // running maxima
+  const int per_sample = blocks_for(n, 256);
+  dim3 grid(per_sample < 96 ? per_sample : 96, B);
+  switch (raw_dtype) {
+#define CB_ZOOM_CASE(DT, T)                                                                                             \
+  case DT:                                                                                                              \
+    if (cubic) cb_launch(zoom_resample_kernel<T, true>, grid, 256, 0, s, (const T*)raw, extent, zoom, out, keys, g, B);  \
+    else cb_launch(zoom_resample_kernel<T, false>, grid, 256, 0, s, (const T*)raw, extent, zoom, out, keys, g, B);       \
+    break;
+    CB_ZOOM_CASE(CB_DT_U8, uint8_t)
+    CB_ZOOM_CASE(CB_DT_I16, int16_t)
+    CB_ZOOM_CASE(CB_DT_U16, uint16_t)
+    default:
+      if (cubic) cb_launch(zoom_resample_kernel<float, true>, grid, 256, 0, s, (const float*)raw, extent, zoom, out, keys, g, B);
+      else cb_launch(zoom_resample_kernel<float, false>, grid, 256, 0, s, (const float*)raw, extent, zoom, out, keys, g, B);
+      break;
+#undef CB_ZOOM_CASE
+  }
+  CB_LAUNCH_CHECK();
+  cb_launch(zoom_scale_kernel, grid, 256, 0, s, out, extent, (const unsigned*)keys, g, B);
   CB_LAUNCH_CHECK();
   return 0;
 }

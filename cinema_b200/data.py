@@ -17,9 +17,16 @@ behind the running step; intensity scaling happens on the device.
                    value that scales to 0, ``drop_last`` batches
     device side    ``scale_intensity``: MONAI ``ScaleIntensity(minv=0, maxv=1)`` = (x - min) / (max - min), constant images
                    map to 0; ``DeviceFeeder`` double-buffers raw batches through pinned memory and a copy stream
+    augmentation   ``RandZoomd`` (prob ``config.transform.prob``, zoom in [0.9, 1.1], keep_size; trilinear for SAX, bicubic
+                   for LAX, one draw shared by the LAX views; cinema/mae/pretrain.py:163-183): the batcher only DRAWS the
+                   per-sample factors, the resampling runs on the device fused with ScaleIntensity and the end padding
+                   (``cb_zoom_intensity``: zoom the unpadded frame about its centre, min / max of the zoomed frame, scale,
+                   zeros outside the frame).  MONAI is not installed here, so this is pinned to MONAI's published ``Zoom``
+                   algorithm restated over ``torch.nn.functional.interpolate`` (``zoom_intensity`` below), not to a MONAI run;
+                   the reference's ``lazy=True`` composition resamples once through an affine grid instead and differs at
+                   the borders.
 
-Not reproduced: ``RandZoomd`` (a probabilistic augmentation, ``config.transform.prob``) and the NIfTI decoder itself
-(SimpleITK is not available here; ``write_shards`` takes arrays).
+Not reproduced: the NIfTI decoder itself (SimpleITK is not available here; ``write_shards`` takes arrays).
 """
 
 from __future__ import annotations
@@ -145,13 +152,17 @@ class ShardSampler:
 # ------------------------------------------------------------------------------------------
 class RawBatch:
     """One batch in the shards' dtype: ``images[view]`` (B, 1, *patch_size) pinned host tensors, ``lo`` / ``hi`` (B,) fp32
-    per view = ScaleIntensity's min / max of each sample's frame."""
+    per view = ScaleIntensity's min / max of each sample's frame.  With the zoom augmentation on: ``extent[view]`` (B, 3)
+    int32 = the frame's own size inside the padded sample (unused axes 1) and ``zoom[view]`` (B,) fp32 = this sample's
+    RandZoom factor (1 = not zoomed)."""
 
-    def __init__(self, images: dict[str, torch.Tensor], lo: dict[str, torch.Tensor], hi: dict[str, torch.Tensor]) -> None:
-        self.images, self.lo, self.hi = images, lo, hi
+    def __init__(self, images: dict[str, torch.Tensor], lo: dict[str, torch.Tensor], hi: dict[str, torch.Tensor],
+                 extent: dict[str, torch.Tensor] | None = None, zoom: dict[str, torch.Tensor] | None = None) -> None:
+        self.images, self.lo, self.hi, self.extent, self.zoom = images, lo, hi, extent, zoom
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for d in (self.images, self.lo, self.hi) for t in d.values())
+        groups = [self.images, self.lo, self.hi] + [d for d in (self.extent, self.zoom) if d is not None]
+        return sum(t.numel() * t.element_size() for d in groups for t in d.values())
 
 
 class FrameBatcher:
@@ -161,8 +172,13 @@ class FrameBatcher:
 
     def __init__(self, dataset: CineShardDataset, sampler: ShardSampler, batch_size: int,
                  image_size_dict: dict[str, tuple[int, ...]], n_frames: int = UKB_N_FRAMES, seed: int | None = None,
-                 pin_memory: bool | None = None, n_buffers: int = 2) -> None:
+                 pin_memory: bool | None = None, n_buffers: int = 2, zoom_prob: float = 0.0,
+                 zoom_range: tuple[float, float] = (0.9, 1.1)) -> None:
+        """``zoom_prob`` > 0 switches the RandZoom augmentation on (``config.transform.prob``; MONAI's default range
+        0.9 - 1.1): per sample one factor for SAX and one shared by the LAX views (two ``RandZoomd`` calls in the
+        reference's Compose), drawn here and applied on the device by ``DeviceFeeder``."""
         self.ds, self.sampler, self.b = dataset, sampler, batch_size
+        self.zoom_prob, self.zoom_range = float(zoom_prob), (float(zoom_range[0]), float(zoom_range[1]))
         self.sizes = {v: tuple(image_size_dict[v]) for v in dataset.views}
         self.n_frames = n_frames
         self.rng = np.random.default_rng(seed)  # cinema/mae/pretrain.py:134 (unseeded there)
@@ -176,7 +192,14 @@ class FrameBatcher:
                 lo[v], hi[v] = torch.empty(batch_size), torch.empty(batch_size)
                 if pin:
                     images[v], lo[v], hi[v] = images[v].pin_memory(), lo[v].pin_memory(), hi[v].pin_memory()
-            self._buffers.append(RawBatch(images, lo, hi))
+            extent = zoom = None
+            if self.zoom_prob > 0.0:
+                extent = {v: torch.ones((batch_size, 3), dtype=torch.int32) for v in dataset.views}
+                zoom = {v: torch.ones(batch_size, dtype=torch.float32) for v in dataset.views}
+                if pin:
+                    extent = {v: t.pin_memory() for v, t in extent.items()}
+                    zoom = {v: t.pin_memory() for v, t in zoom.items()}
+            self._buffers.append(RawBatch(images, lo, hi, extent, zoom))
         self._next = 0
 
     def __len__(self) -> int:
@@ -185,6 +208,12 @@ class FrameBatcher:
     def _fill(self, out: RawBatch, indices: list[int]) -> RawBatch:
         for j, idx in enumerate(indices):
             t = int(self.rng.integers(self.n_frames))  # ONE frame index per sample, shared by its views
+            z3 = z2 = 1.0
+            if self.zoom_prob > 0.0:  # RandZoomd(keys="sax") then RandZoomd(keys=lax views): one Bernoulli + one factor each
+                if self.rng.random() < self.zoom_prob:
+                    z3 = float(np.float32(self.rng.uniform(*self.zoom_range)))
+                if self.rng.random() < self.zoom_prob:
+                    z2 = float(np.float32(self.rng.uniform(*self.zoom_range)))
             for v in self.ds.views:
                 frame, mn, mx = self.ds.frame(idx, v, t)
                 size = self.sizes[v]
@@ -195,6 +224,9 @@ class FrameBatcher:
                     dst[...] = np.asarray(mn).astype(dst.dtype)  # scales to 0: SpatialPad runs after ScaleIntensity
                 dst[tuple(slice(0, a) for a in frame.shape)] = frame
                 out.lo[v][j], out.hi[v][j] = mn, mx
+                if out.zoom is not None:
+                    out.zoom[v][j] = z3 if frame.ndim == 3 else z2
+                    out.extent[v][j] = torch.tensor(list(frame.shape) + [1] * (3 - frame.ndim), dtype=torch.int32)
         return out
 
     def __iter__(self) -> Iterator[RawBatch]:
@@ -219,6 +251,38 @@ def scale_intensity(raw: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, out: 
     return res.mul_(inv)
 
 
+def zoom_intensity(raw: torch.Tensor, extent: torch.Tensor, zoom: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """RandZoom(keep_size) -> ScaleIntensity -> SpatialPad("end") restated in torch: the CPU feeder's path and the reference
+    the CUDA kernel (``cb_zoom_intensity``) is tested against.  MONAI ``Zoom`` (monai/transforms/spatial/functional.py
+    ``zoom``): ``interpolate(frame, scale_factor=z, mode, align_corners=False)`` (trilinear for 3-D frames, bicubic for
+    2-D), then per axis pad ``[half, diff - half]`` zeros or slice ``[half, half + size)`` with ``half = |diff| // 2`` back
+    to the frame's own size; ScaleIntensity over the zoomed frame; zeros outside the frame.
+    raw (B, 1, *size), extent (B, 3) int, zoom (B,) fp32."""
+    import torch.nn.functional as F
+
+    nd = raw.dim() - 2
+    res = torch.zeros(raw.shape, dtype=torch.float32, device=raw.device) if out is None else out.zero_()
+    for j in range(raw.shape[0]):
+        e = [int(x) for x in extent[j, :nd]]
+        z = float(zoom[j])
+        box = tuple(slice(0, a) for a in e)
+        img = raw[j, 0][box].to(torch.float32)
+        if z != 1.0:
+            zoomed = F.interpolate(img[None, None], scale_factor=[z] * nd, mode="trilinear" if nd == 3 else "bicubic",
+                                   align_corners=False)[0, 0]
+            pads, cut = [], []
+            for od, zd in zip(e, zoomed.shape):
+                diff, half = od - zd, abs(od - zd) // 2
+                pads.append((half, diff - half) if diff > 0 else (0, 0))
+                cut.append(slice(half, half + od) if diff < 0 else slice(None))
+            zoomed = F.pad(zoomed, [p for pr in reversed(pads) for p in pr])[tuple(cut)]
+        else:
+            zoomed = img
+        lo, hi = zoomed.min(), zoomed.max()
+        res[j, 0][box] = (zoomed - lo) / (hi - lo) if float(hi) > float(lo) else torch.zeros_like(zoomed)
+    return res
+
+
 class DeviceFeeder:
     """Raw batches -> fp32 device batches for ``MAETrainer.step``: every ``RawBatch`` is uploaded on a copy stream into
     one of two device staging sets (overlapping the step in flight), then scaled on the compute stream.  Iterating yields
@@ -241,20 +305,32 @@ class DeviceFeeder:
                 "out": {v: torch.empty(t.shape, dtype=torch.float32, device=self.dev) for v, t in raw.images.items()},
                 "free": torch.cuda.Event() if self.cuda else None,
             })
+            if raw.zoom is not None:
+                self._slots[-1]["extent"] = {v: torch.empty(t.shape, dtype=t.dtype, device=self.dev) for v, t in raw.extent.items()}
+                self._slots[-1]["zoom"] = {v: torch.empty(t.shape, dtype=t.dtype, device=self.dev) for v, t in raw.zoom.items()}
+                self._slots[-1]["keys"] = {v: torch.empty(2 * t.shape[0], dtype=torch.int32, device=self.dev) for v, t in raw.zoom.items()}
         return self._slots[k]
+
+    @staticmethod
+    def _groups(raw: RawBatch):
+        g = [("img", raw.images), ("lo", raw.lo), ("hi", raw.hi)]
+        if raw.zoom is not None:
+            g += [("extent", raw.extent), ("zoom", raw.zoom)]
+        return g
 
     def _upload(self, k: int, raw: RawBatch):
         slot = self._slot(k, raw)
         self.h2d_bytes_per_batch = raw.nbytes()
+        slot["zoomed"] = raw.zoom is not None
         if not self.cuda:
-            for name, src in (("img", raw.images), ("lo", raw.lo), ("hi", raw.hi)):
+            for name, src in self._groups(raw):
                 for v, t in src.items():
                     slot[name][v].copy_(t)
             return slot, None
         ready = torch.cuda.Event()
         with torch.cuda.stream(self._copy):
             self._copy.wait_event(slot["free"])  # the scale kernels that last read this slot have run
-            for name, src in (("img", raw.images), ("lo", raw.lo), ("hi", raw.hi)):
+            for name, src in self._groups(raw):
                 for v, t in src.items():
                     slot[name][v].copy_(t, non_blocking=True)
             ready.record(self._copy)
@@ -268,10 +344,14 @@ class DeviceFeeder:
 
             out = {}
             for v, img in slot["img"].items():
-                if img.dtype in _C._RAW_DT and (img[0].numel() * img.element_size()) % 16 == 0:
+                if slot["zoomed"]:  # RandZoom + ScaleIntensity + end padding in two passes (cb_zoom_intensity); no torch path
+                    out[v] = _C.zoom_intensity(img, slot["extent"][v], slot["zoom"][v], slot["out"][v], slot["keys"][v])
+                elif img.dtype in _C._RAW_DT and (img[0].numel() * img.element_size()) % 16 == 0:
                     out[v] = _C.scale_intensity(img, slot["lo"][v], slot["hi"][v], slot["out"][v])
                 else:  # odd sample sizes / dtypes keep the two-kernel torch form
                     out[v] = scale_intensity(img, slot["lo"][v], slot["hi"][v], out=slot["out"][v])
+        elif slot["zoomed"]:
+            out = {v: zoom_intensity(slot["img"][v], slot["extent"][v], slot["zoom"][v], out=slot["out"][v]) for v in slot["img"]}
         else:
             out = {v: scale_intensity(slot["img"][v], slot["lo"][v], slot["hi"][v], out=slot["out"][v]) for v in slot["img"]}
         if self.cuda:

@@ -41,7 +41,10 @@ def get_feeder(config, device, rank: int = 0, world: int = 1) -> D.DeviceFeeder:
     sizes = {v: tuple(c.data.sax.patch_size if v == "sax" else c.data.lax.patch_size) for v in views}
     ds = D.CineShardDataset(c.data.shard_dir, views=views)
     sampler = D.ShardSampler(len(ds), rank=rank, world=world, seed=c.seed)
-    batcher = D.FrameBatcher(ds, sampler, batch_size=c.train.batch_size, image_size_dict=sizes, seed=c.seed + rank)
+    tr = config.get("transform") if isinstance(config, dict) else getattr(config, "transform", None)
+    zoom_prob = float((tr.get("prob", 0.0) if isinstance(tr, dict) else getattr(tr, "prob", 0.0)) if tr is not None else 0.0)
+    batcher = D.FrameBatcher(ds, sampler, batch_size=c.train.batch_size, image_size_dict=sizes, seed=c.seed + rank,
+                             zoom_prob=zoom_prob)  # RandZoomd(prob=config.transform.prob), cinema/mae/pretrain.py:163-183
     return D.DeviceFeeder(batcher, device)
 
 

@@ -146,8 +146,6 @@ int cb_embed_rows_f32(const float* a, long long a_bstride, long long a_off, cons
  * the backward of the broadcast in cinema/vit.py:672 and cinema/mae/mae.py:98-99. */
 int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int B, int k, int D, float* out,
                       void* stream);
-/* dst[i] = bf16(src[i] * scale * f), f = 1 (scale_dev NULL), *scale_dev (group == 0) or scale_dev[i / group] (group > 0,
- * a multiple of 4 dividing n: per-sample factors, the backward of DropPath, cinema/vit.py:606,608) */
 /* Input pipeline, device side: MONAI ScaleIntensity(minv=0, maxv=1) of a raw-dtype batch in ONE pass (the `ScaleIntensityd`
  * of cinema/mae/pretrain.py:184 applied after the upload instead of on 16 CPU workers):
  *   out[b, i] = (float(raw[b, i]) - lo[b]) * inv[b],  inv[b] = hi[b] > lo[b] ? 1 / (hi[b] - lo[b]) : 0   (fp32)
@@ -155,6 +153,17 @@ int cb_colsum_seg_f32(const float* X, long long bstride_rows, long long off, int
  * lo / hi: fp32 [B] per-sample minimum / maximum (the shard index carries them); a constant sample maps to 0. */
 int cb_scale_intensity(const void* raw, int raw_dtype, const float* lo, const float* hi, float* out, int B,
                        long long n_per_sample, void* stream);
+/* Input pipeline, device side, augmented: RandZoom(keep_size) -> ScaleIntensity -> SpatialPad("end") in two passes
+ * (`RandZoomd` trilinear for SAX / bicubic for LAX, `ScaleIntensityd`, `SpatialPadd`: cinema/mae/pretrain.py:163-199; MONAI
+ * `Zoom` = torch `interpolate(scale_factor, align_corners=False)` of the unpadded frame, centre-padded with zeros / centre-
+ * cropped back to its own size).  raw: B frames of raw_dtype stored in the model's input size `size[nd]` (host array; the
+ * frame occupies the corner [0, extent[b]) of it); extent: int32 [B][3] device (per-sample frame size, unused axes 1);
+ * zoom: fp32 [B] device (1 = identity, bit-exact); out: fp32 [B][prod size]; keys_ws: 2 * B uint32 device scratch (per-
+ * sample min / max of the zoomed frame).  nd = 3 && cubic = 0 (trilinear) or nd = 2 && cubic = 1 (bicubic, A = -0.75). */
+int cb_zoom_intensity(const void* raw, int raw_dtype, const int* extent, const float* zoom, float* out, void* keys_ws,
+                      int B, int nd, const int* size, int cubic, void* stream);
+/* dst[i] = bf16(src[i] * scale * f), f = 1 (scale_dev NULL), *scale_dev (group == 0) or scale_dev[i / group] (group > 0,
+ * a multiple of 4 dividing n: per-sample factors, the backward of DropPath, cinema/vit.py:606,608) */
 int cb_scale_cast_bf16(const float* src, void* dst, long long n, const float* scale_dev, float scale, long long group,
                        void* stream);
 

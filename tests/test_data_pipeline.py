@@ -138,6 +138,53 @@ def test_device_feeder_yields_every_batch_in_order(shard_root):
             assert float(b[v].min()) == 0.0 and float(b[v].max()) <= 1.0 + 1e-6
 
 
+def test_zoom_identity_and_keep_size_restatement():
+    """``zoom_intensity`` (the torch restatement of RandZoom(keep_size) -> ScaleIntensity -> SpatialPad): factor 1 equals
+    plain ScaleIntensity of the frame, zoom-out centre-pads with zeros, zoom-in keeps the centre, the model-size padding
+    stays 0, and every sample lands in [0, 1] with both ends reached."""
+    g = torch.Generator().manual_seed(0)
+    raw = torch.zeros(3, 1, 24, 20, 6, dtype=torch.int16)
+    ext = torch.tensor([[20, 18, 5], [24, 20, 6], [16, 16, 4]], dtype=torch.int32)
+    for j in range(3):
+        e = ext[j].tolist()
+        raw[j, 0, :e[0], :e[1], :e[2]] = torch.randint(5, 900, tuple(e), generator=g, dtype=torch.int16)
+    zoom = torch.tensor([1.0, 0.93, 1.1], dtype=torch.float32)
+    out = D.zoom_intensity(raw, ext, zoom)
+    f0 = raw[0, 0, :20, :18, :5].float()
+    assert torch.equal(out[0, 0, :20, :18, :5], (f0 - f0.min()) / (f0.max() - f0.min()))
+    for j in range(3):
+        e = ext[j].tolist()
+        inside = out[j, 0, :e[0], :e[1], :e[2]]
+        assert float(inside.min()) == 0.0 and abs(float(inside.max()) - 1.0) < 1e-6
+        assert float(out[j].sum()) == pytest.approx(float(inside.sum()))  # nothing outside the frame
+    # zoom 0.93 of a 24 x 20 x 6 frame: 22 x 18 x 5 voxels centred -> pads (1, 1), (1, 1), (0, 1): the border planes hold the
+    # zoomed frame's zero padding, which is also its minimum (raw values are >= 5), i.e. ScaleIntensity's 0
+    z = out[1, 0]
+    assert float(z[0].abs().max()) == 0.0 and float(z[23].abs().max()) == 0.0 and float(z[:, :, 5].abs().max()) == 0.0
+    assert float(z[:, 0].abs().max()) == 0.0 and float(z[:, 19].abs().max()) == 0.0
+    assert float(z[1:23, 1:19, :5].min()) > 0.0
+
+
+def test_batcher_draws_zoom_factors_and_feeder_applies_them(shard_root):
+    ds = D.CineShardDataset(shard_root)
+    sizes = {"sax": (24, 24, 8), "lax_2c": (32, 32), "lax_3c": (32, 32), "lax_4c": (32, 32)}
+    mk = lambda p: D.FrameBatcher(ds, D.ShardSampler(len(ds), seed=4), 2, sizes, n_frames=6, seed=9, pin_memory=False, zoom_prob=p)  # noqa: E731
+    raws = [(r.zoom["sax"].clone(), r.zoom["lax_2c"].clone(), r.zoom["lax_3c"].clone(), r.extent["sax"].clone(),
+             r.extent["lax_4c"].clone()) for r in mk(1.0)]
+    assert len(raws) == 3
+    for zs, z2, z3, es, el in raws:
+        assert torch.equal(z2, z3)                                     # one draw for the LAX views of a sample
+        assert ((zs >= 0.9) & (zs <= 1.1)).all() and not torch.equal(zs, z2)
+        assert es.tolist() == [[20, 24, 5]] * 2 and el.tolist() == [[28, 30, 1]] * 2
+    assert all(float(r.zoom["sax"].min()) == 1.0 == float(r.zoom["sax"].max()) for r in mk(1e-9))  # prob ~ 0: never zoomed
+    assert next(iter(mk(0.0))).zoom is None
+    fed = [{v: t.clone() for v, t in b.items()} for b in D.DeviceFeeder(mk(1.0), "cpu")]  # (the feeder recycles its slots)
+    direct = [{v: D.zoom_intensity(r.images[v], r.extent[v], r.zoom[v]).clone() for v in r.images} for r in mk(1.0)]
+    for a, b in zip(direct, fed):
+        for v in a:
+            assert torch.equal(a[v], b[v]) and float(b[v].min()) == 0.0 and float(b[v].max()) <= 1.0 + 1e-6
+
+
 def test_pipeline_feeds_the_model(shard_root, emulated_kernels, golden_dir):
     """The feeder's batches go straight into the model (host logic through the emulated kernels)."""
     from cinema_b200 import CineMA

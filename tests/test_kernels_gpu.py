@@ -614,3 +614,43 @@ def test_scale_intensity_kernel(dtype):
     ref = scale_intensity(raw.to(torch.float32) if dtype == torch.uint16 else raw, lo, hi)
     assert torch.equal(out.cpu(), ref)
     assert float(out[2].abs().max()) == 0.0 and float(out.max()) == 1.0 and float(out.min()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int16, torch.float32])
+@pytest.mark.parametrize("nd", [3, 2])
+def test_zoom_intensity_kernel(dtype, nd):
+    """cb_zoom_intensity (RandZoom keep_size -> ScaleIntensity -> SpatialPad "end", cinema/mae/pretrain.py:163-199) against
+    MONAI's Zoom algorithm restated over torch's own interpolate on the same device (data.zoom_intensity): trilinear for 3-D
+    frames, bicubic for 2-D; zoom factors below / above 1, the identity (bit-exact), frames smaller than the padded sample,
+    a constant frame.  fp32 tolerance: the two resamplers differ in FMA contraction only; ScaleIntensity divides by the range."""
+    from cinema_b200.data import scale_intensity, zoom_intensity
+
+    g = torch.Generator().manual_seed(3)
+    size = (40, 36, 10) if nd == 3 else (48, 44)
+    ext = [[40, 36, 10], [33, 36, 7], [40, 29, 10], [17, 20, 5], [40, 36, 10], [30, 30, 8]] if nd == 3 else \
+          [[48, 44, 1], [41, 44, 1], [48, 37, 1], [20, 23, 1], [48, 44, 1], [30, 30, 1]]
+    b = len(ext)
+    raw = torch.zeros(b, 1, *size)
+    for j, e in enumerate(ext):
+        box = tuple(slice(0, a) for a in e[:nd])
+        raw[j, 0][box] = torch.rand(tuple(e[:nd]), generator=g) * (250 if dtype == torch.uint8 else 2000) + 3
+    raw[5] = 0
+    raw[5, 0][tuple(slice(0, a) for a in ext[5][:nd])] = 9  # a constant frame
+    raw = raw.floor().to(dtype) if dtype != torch.float32 else raw
+    zoom = torch.tensor([1.0, 0.9, 1.1, 0.937, 1.063, 1.0], dtype=torch.float32)
+    extent = torch.tensor(ext, dtype=torch.int32)
+    out = torch.full(raw.shape, -7.0, device=DEV, dtype=torch.float32)
+    _C.zoom_intensity(raw.to(DEV), extent.to(DEV), zoom.to(DEV), out)
+    ref = zoom_intensity(raw.to(DEV), extent, zoom)  # torch's CUDA interpolate
+    assert float((out - ref).abs().max()) < 2e-5
+    # identity: exactly ScaleIntensity of the frame
+    f0 = raw[0:1].to(torch.float32)
+    lo, hi = f0.min().reshape(1), f0.max().reshape(1)
+    assert torch.equal(out[0:1].cpu(), scale_intensity(f0, lo, hi))
+    for j, e in enumerate(ext):
+        box = tuple(slice(0, a) for a in e[:nd])
+        inside = out[j, 0][box]
+        assert float(out[j].sum()) == pytest.approx(float(inside.sum()), rel=1e-6)  # zeros outside the frame
+        if j != 5:
+            assert float(inside.min()) == 0.0 and float(inside.max()) == pytest.approx(1.0, abs=1e-6)
+    assert float(out[5].abs().max()) == 0.0  # a constant frame (not zoomed) maps to 0

@@ -560,7 +560,9 @@ def test_trainer_prefetch_equals_direct_upload(golden_dir):
                 tr.prefetch(batches[i + 1])
             out.append(float(loss))
         losses[mode] = out
-    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(losses["direct"], losses["prefetch"]))  # atomics reorder sums
+    # the two runs differ only through the order of fp32 atomics (split-K / bias-gradient accumulation), which five AdamW steps
+    # amplify to ~1e-5 of the loss (one run in six exceeded 1e-5); a wrong or stale batch would show up at the 1e-2 level
+    assert all(abs(a - b) <= 5e-4 * abs(a) for a, b in zip(losses["direct"], losses["prefetch"])), losses
     assert len(set(losses["direct"])) == len(batches)  # the batches really differ
 
 

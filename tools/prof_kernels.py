@@ -64,6 +64,17 @@ def build(only):
         md, nd_, kd = 32848, 2048, 512
         xd, dyd, dwd = rn(md, kd, dtype=BF), rn(md, nd_, dtype=BF), torch.zeros(nd_, kd, device=DEV)
         K.append(("gemm wgrad fc1 dec", mk(_C.gemm, dyd, xd, dwd, a_mn=True, b_mn=True, accumulate=True), 0, 2.0 * md * nd_ * kd))
+        # decoder (D = 512): the short-K shapes
+        xq, wq, bq = rn(md, kd, dtype=BF), rn(nd_, kd, dtype=BF, scale=0.02), rn(nd_)
+        yq, yq2 = torch.empty(md, nd_, device=DEV, dtype=BF), torch.empty(md, nd_, device=DEV, dtype=BF)
+        K.append(("gemm fc1+gelu dec", mk(_C.gemm, xq, wq, yq, out2=yq2, bias=bq, epilogue=_C.EPI_GELU), 0, 2.0 * md * nd_ * kd))
+        wq2, auxq = rn(kd, nd_, dtype=BF, scale=0.02), rn(md, nd_, dtype=BF)
+        K.append(("gemm fc2 dgrad gelu' dec", mk(_C.gemm, xq, wq2, yq, b_mn=True, aux=auxq, epilogue=_C.EPI_GELU_BWD), 0, 2.0 * md * nd_ * kd))
+        wp, yp = rn(kd, kd, dtype=BF, scale=0.02), torch.empty(md, kd, device=DEV, dtype=BF)
+        K.append(("gemm q-proj dec 512x512", mk(_C.gemm, xq, wp, yp, bias=rn(kd)), 0, 2.0 * md * kd * kd))
+        K.append(("gemm dgrad dec 512x512", mk(_C.gemm, xq, wp, yp, b_mn=True), 0, 2.0 * md * kd * kd))
+        resq = rn(md, kd)
+        K.append(("gemm proj+res dec 512x512", mk(_C.gemm, xq, wp, resq, bias=rn(kd), residual=resq), 0, 2.0 * md * kd * kd))
         xs, ws, ys = rn(147456, 64, dtype=BF), rn(256, 64, dtype=BF), torch.empty(147456, 256, device=DEV, dtype=BF)
         ys2, bs = torch.empty(147456, 256, device=DEV, dtype=BF), rn(256)
         K.append(("gemm stem fc1+gelu 147456x256x64", mk(_C.gemm, xs, ws, ys, out2=ys2, bias=bs, epilogue=_C.EPI_GELU), 147456 * (64 + 512) * 2, 2.0 * 147456 * 256 * 64))
