@@ -95,6 +95,24 @@ def measured_peaks() -> tuple[dict, str]:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def measured_write_gbs(dev) -> float:
+    """HBM WRITE bandwidth, measured live: a 1 GiB fill (no reads), best of 6.  The copy figure of MEASURED_PEAKS.json counts
+    read + write bytes; a kernel that mostly writes (fc1 + GELU stores two bf16 outputs per accumulator element) is bounded
+    by this number instead (profiles/r02_gemm_epilogue.md)."""
+    buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+    best = 0.0
+    for i in range(7):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        buf.fill_(float(i))
+        e.record()
+        torch.cuda.synchronize()
+        if i:
+            best = max(best, buf.numel() * 4 / (s.elapsed_time(e) * 1e-3) / 1e9)
+    del buf
+    return round(best, 1)
+
+
 def synthetic_batch(kw: dict, b: int, seed: int, pin: bool) -> dict:
     """Images in [0, 1) like ScaleIntensityd (cinema/mae/pretrain.py:184)."""
     g = torch.Generator().manual_seed(seed)
@@ -293,26 +311,31 @@ def instrumented_step(trainer, batch_dev: dict) -> dict:
         agg[name] = v
     own = sum(a[0] for a in agg.values())
     peaks, _ = measured_peaks()
+    write_gbs = measured_write_gbs(next(iter(batch_dev.values())).device)
 
     def shape_roof(tag: str, ms: float, launches: int, flops: float) -> dict:
         """Which roof bounds this GEMM shape?  Algorithmic bytes: A + B (bf16) + the stored output (+ the fp32 residual it
         reads, + the bf16 GELU' operand, + the second bf16 output of the GELU flavour); split-K accumulation reads and
-        writes the fp32 output."""
+        writes the fp32 output.  Three candidate times: tensor (sustained bf16 peak), all bytes at the copy bandwidth, and
+        the WRITTEN bytes at the write bandwidth measured above (a fill)."""
         f = dict(kv.split("=") for kv in tag.split()[3:])
         m, n, k = (int(x[1:]) for x in tag.split()[:3])
         o32, res, epi, acc = int(f["o32"]), int(f["res"]), int(f["epi"]), int(f["acc"])
         by = 2.0 * (m * k + n * k) + m * n * (4 if o32 else 2) * (2 if acc else 1) + res * 4.0 * m * n
         by += 2.0 * m * n if epi in (1, 2) else 0.0
+        wr = m * n * (4.0 if o32 else 2.0) + (2.0 * m * n if epi == 1 else 0.0)
         t_hbm = by / (peaks["hbm_gbs"] * 1e9)
+        t_wr = wr / (write_gbs * 1e9) if write_gbs > 0 else 0.0
         t_tc = (flops / launches) / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 1e12)
         t = ms / launches / 1e3
-        bound = "hbm" if t_hbm > t_tc else "tensor"
-        return {"bound": bound, "frac_of_bound": round(max(t_hbm, t_tc) / t, 3), "gb_per_s": round(by / t / 1e9, 0)}
+        bound, t_b = max((("tensor", t_tc), ("hbm", t_hbm), ("hbm-write", t_wr)), key=lambda kv: kv[1])
+        return {"bound": bound, "frac_of_bound": round(t_b / t, 3), "gb_per_s": round(by / t / 1e9, 0),
+                "written_gb_per_s": round(wr / t / 1e9, 0)}
 
     top_shapes = [{"gemm": k, "launches": v[2], "ms": round(v[0], 3), "tflops": round(v[1] / v[0] / 1e9, 1),
                    **shape_roof(k, v[0], v[2], v[1])}
                   for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:24]]
-    return {"step_ms": total, "own_kernels_ms": own, "own_kernels_eager_events_ms": eager_own,
+    return {"step_ms": total, "own_kernels_ms": own, "own_kernels_eager_events_ms": eager_own, "hbm_write_gbs": write_gbs,
             "note": "one eager step on a single stream records every C-ABI launch; the per-kernel times are CUDA events around "
                     "each launch of a REPLAY of those calls in order, queued behind a GPU-side sleep (device time only, no "
                     "host gaps); step_ms is the host-bound eager step and is not a throughput figure",
