@@ -33,6 +33,7 @@ _SIGNATURES = {
     "cb_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cb_set_pdl": (c_int, [c_int]),
     "cb_attention_trace": (c_int, [c_void_p]),
+    "cb_gemm_trace": (c_int, [c_void_p]),
     "cb_scale_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "cb_zoom_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_void_p]),

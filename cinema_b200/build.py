@@ -41,6 +41,10 @@ def find_nvcc() -> str:
     return cand
 
 
+if os.environ.get("CB_GEMM_TRACE") == "1":  # diagnostics build: in-kernel clock stamps in the GEMM (tools/gemm_trace.py)
+    NVCC_FLAGS.append("-DCB_GEMM_TRACE")
+
+
 def _digest(paths: list[Path]) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):

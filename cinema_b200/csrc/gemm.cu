@@ -21,7 +21,40 @@
 #include <cstdlib>
 #include <type_traits>
 
+// In-kernel clock trace (diagnostics, cb_gemm_trace; same idea as cb_attention_trace): when a device buffer is registered,
+// the leader CTA of one pair in the middle of the grid stamps clock64() at the phase boundaries of its producer warp, its MMA
+// warp and its first epilogue warp for the first eight tiles it processes (slot layout: tools/gemm_trace.py).
+// The stamps cost registers in the epilogue warps (56 bytes of spills, +15 % on the short-K launches), so they are compiled
+// in only with -DCB_GEMM_TRACE (CB_GEMM_TRACE=1 python -m cinema_b200.build --force); the entry point always exists.
+#ifdef CB_GEMM_TRACE
+__device__ long long* g_gemm_trace = nullptr;
+#endif
+
+extern "C" int cb_gemm_trace(long long* device_buf) {
+#ifdef CB_GEMM_TRACE
+  CB_CUDA(cudaMemcpyToSymbol(g_gemm_trace, &device_buf, sizeof(device_buf)));
+  return 0;
+#else
+  CB_CHECK_ARG(device_buf == nullptr, "gemm_trace: the library was built without -DCB_GEMM_TRACE");
+  return 0;
+#endif
+}
+
 namespace {
+
+#ifdef CB_GEMM_TRACE
+#define CB_GTR(slot)                      \
+  do {                                    \
+    if (tron) trace[(slot)] = clock64();  \
+  } while (0)
+#define CB_GTRE(slot)                              \
+  do {                                             \
+    if (tre && ti < 8) trace[(slot)] = clock64();  \
+  } while (0)
+#else
+#define CB_GTR(slot) do {} while (0)
+#define CB_GTRE(slot) do {} while (0)
+#endif
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -86,6 +119,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef CB_GEMM_TRACE
+  long long* const trace = g_gemm_trace;
+  const bool tron = trace != nullptr && lane == 0 && blockIdx.x == ((gridDim.x / 2) & ~1u);
+#endif
+  if (warp == 0) CB_GTR(1000);
 
   pdl_launch_dependents();  // the next kernel may be scheduled as SMs drain; it waits for this grid before reading
   if (warp == 0 && lane == 0) {
@@ -114,6 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // barriers, TMEM and descriptors are set up: now wait for the producer kernels of A / B / residual
+  if (warp == 0) CB_GTR(1001);
 
   const int tiles = p.num_m_tiles * p.num_n_tiles;  // pair: num_m_tiles counts 256-row tiles
   const int items = tiles * p.splits;
@@ -130,7 +169,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = worker; item < items; item += n_workers) {
+      [[maybe_unused]] int ti = 0;
+      for (int item = worker; item < items; item += n_workers, ++ti) {
         const int split = item % p.splits;
         const int tile = item / p.splits;
         const int n_tile = tile % p.num_n_tiles;
@@ -141,6 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);     // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (ti < 8 && kb - kb0 < 16) CB_GTR(64 * ti + (kb - kb0));
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           if (leader) {
@@ -184,15 +225,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = worker; item < items; item += n_workers) {
+      [[maybe_unused]] int ti = 0;
+      for (int item = worker; item < items; item += n_workers, ++ti) {
         const int split = item % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (ti < 8) CB_GTR(64 * ti + 32);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (ti < 8 && kb - kb0 < 16) CB_GTR(64 * ti + 16 + (kb - kb0));
           tcgen05_fence_after();
           if (leader) {
             const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -209,6 +253,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (kb + 1 == kb1) umma_commit_g<CTAS>(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
           }
           __syncwarp();
+          if (ti < 8 && kb + 1 == kb1) CB_GTR(64 * ti + 33);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -249,6 +294,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     bf16* const out16 = reinterpret_cast<bf16*>(p.out);
     int acc = 0;
     uint32_t acc_phase = 0;
+#ifdef CB_GEMM_TRACE
+    int ti = 0;
+    const bool tre = tron && ew == 0;
+#endif
     float4 pre_res[4];
     uint2 pre_aux[4];
 #pragma unroll
@@ -307,7 +356,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
       }
+      CB_GTRE(64 * ti + 40);
       mbar_wait(&tfull_bar[acc], acc_phase);
+      CB_GTRE(64 * ti + 41);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
@@ -393,6 +444,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           if (sub == 0 && col_ok) red_add_v4(p.colsum + col, cs[0], cs[1], cs[2], cs[3]);
         }
+        CB_GTRE(64 * ti + 42 + c);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -400,6 +452,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (PAIR && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's barrier gates the MMAs
         else mbar_arrive(&tempty_bar[acc]);
       }
+      CB_GTRE(64 * ti + 50);
+#ifdef CB_GEMM_TRACE
+      ++ti;
+#endif
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -417,9 +473,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   }
 
+  if (warp == 0) CB_GTR(1002);
   tcgen05_fence_before();
   if constexpr (PAIR) cluster_sync();  // no CTA of the pair leaves (or frees TMEM) while its peer may still touch it
   else __syncthreads();
+  if (warp == 0) CB_GTR(1003);
   if (warp == 1) {
     tcgen05_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);

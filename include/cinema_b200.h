@@ -253,6 +253,9 @@ int cb_set_pdl(int enabled);
  * its softmax / compute warps and of its MMA-issuing warp (slot layout and reader: tools/attn_trace.py).  This is how
  * profiles/r0x_attention_clock_trace.md is produced; it is not part of any product path. */
 int cb_attention_trace(long long* device_buf);
+/* Diagnostics only, as cb_attention_trace: the leader CTA of one pair in the middle of every cb_gemm_bf16 launch stamps
+ * clock64() at the phase boundaries of its producer, MMA and first epilogue warp (1024 x int64, tools/gemm_trace.py). */
+int cb_gemm_trace(long long* device_buf);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from cinema_b200 import _C
 from tools.perf_gemm import timeit
 DEV = "cuda"
-m, n, k = 10960, 3072, 768
+m, n, k = (32848, 2048, 512) if "--dec" in sys.argv else (10960, 3072, 768)
+print(f"M {m} N {n} K {k}")
 dy = torch.randn(m, k, device=DEV).bfloat16()
 w = (torch.randn(k, n, device=DEV) * 0.02).bfloat16()
 wk = (torch.randn(n, k, device=DEV) * 0.02).bfloat16()
