@@ -79,6 +79,7 @@ struct GemmArgs {
   float* colsum;  // optional: column sums of the bf16 output (bias gradient of the consumer)
   const float* row_scale;  // optional: per row-group factor on (alpha * acc + bias) before the residual (stochastic depth)
   int rows_per_group;
+  int wide;  // wide-store epilogue path allowed (CB_GEMM_WIDE, default 1)
   // CONV instantiations only (appended: the layout seen by the GEMM instantiations is unchanged): K = taps * C_in, the A
   // tile of k-block kb is the 2-D box of the [rows, C_in] tensor map at row m0 + conv_off[kb / conv_kb_per_tap]
   int conv_kb_per_tap;
@@ -93,9 +94,14 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN / CTAS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  // WIDE: the 256-wide pair kernel (every hot launch of the step) has a second epilogue path for plain bf16 outputs that
+  // stores full 128-byte row segments (run_tile_wide below); its per-warp staging tile is 32 rows x 128 B, paid for with one
+  // pipeline stage (five instead of six: the long-K launches measured the same)
+  static constexpr bool WIDE = CTAS == 2 && BN == 256;
+  static constexpr int STAGES = CTAS == 2 ? (BN == 256 ? 5 : 8) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = BN == 256 ? 512 : (BN == 128 ? 256 : 128);
-  static constexpr int STAGING_BYTES = EPI_WARPS * 2048;  // per-warp 32 x 16 fp32 epilogue transposition tile
+  static constexpr int STAGING_PER_WARP = WIDE ? 4096 : 2048;  // 32 x 16 fp32 transposition tile / 32 x 64 bf16 output tile
+  static constexpr int STAGING_BYTES = EPI_WARPS * STAGING_PER_WARP;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -279,7 +285,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int cq = ew >> 2;    // which quarter of the tile's columns
     constexpr int COLS_PER_WARP = BN / 4;
     constexpr int CHUNKS = COLS_PER_WARP / 16;
-    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + ew * 2048);
+    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + ew * C::STAGING_PER_WARP);
     const int sub = lane >> 2;  // row inside a group of eight
     const int c16 = lane & 3;   // 16-byte column (4 fp32) inside the 16-column chunk
     const bool has_res = p.residual != nullptr;
@@ -461,8 +467,104 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         acc_phase ^= 1;
       }
     };
+
+    // ---- wide-store path (256-wide pair kernel, plain bf16 output: no residual / second output / column sums / row scale).
+    // The in-kernel clock trace (profiles/r02_gemm_clock_trace.md) showed the epilogue of the short-K launches bound by the
+    // NUMBER of global store requests: every STG of the path above covers eight rows x 32 bytes = eight requests; a plain
+    // bf16 tile took 1.5 k clocks per 16-column chunk, 7.5 k per tile against 4.3 k clocks of MMA at K = 512.  Here the
+    // arithmetic runs in the accumulator's own layout (thread == row, 16 consecutive columns per chunk, the bias is a
+    // warp-uniform load), the packed bf16 rows of all four chunks are collected in a 128B-swizzled [32 rows x 128 B] tile
+    // per warp and leave as 16-byte vectors covering whole 128-byte row segments: 4 x fewer requests, 3.3 k clocks per tile
+    // (K = 512, N = 2048: 71.7 -> 61.4 us).  The accumulator stage goes back to the MMA warp as soon as its last chunk is in
+    // registers.  (The GELU flavours did NOT profit from the same treatment -- their epilogue is bound by instruction issue
+    // and the MUFU pipe, 1.85 k clocks of arithmetic per chunk -- and stay on the path above.)
+    auto run_tile_wide = [&](int item) {
+      const int tile = item / p.splits;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int row0 = m_tile * TILE_M + (int)cta_rank * BM + q * 32;  // first row of this warp
+      const int col0 = n_tile * BN + cq * COLS_PER_WARP;               // first column of this warp
+      const uint32_t my_row = stg + lane * 128;                        // this thread's row of the staging tile
+      const uint32_t sw = (uint32_t)(lane & 7);
+      CB_GTRE(64 * ti + 40);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      CB_GTRE(64 * ti + 41);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cq * COLS_PER_WARP;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr0 + c * 16, r);
+        const int col = col0 + c * 16;
+        float4 b4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          b4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_bias && col + 4 * k < p.N) b4[k] = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * k));
+        }
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {  // the accumulator is in registers: release the stage before the last chunk's arithmetic
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[2 * k] = pack_bf16(fmaf(__uint_as_float(r[4 * k + 0]), p.alpha, b4[k].x), fmaf(__uint_as_float(r[4 * k + 1]), p.alpha, b4[k].y));
+          w[2 * k + 1] = pack_bf16(fmaf(__uint_as_float(r[4 * k + 2]), p.alpha, b4[k].z), fmaf(__uint_as_float(r[4 * k + 3]), p.alpha, b4[k].w));
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2)  // 16 columns = 32 bytes = units 2c, 2c + 1 of this thread's row
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((((uint32_t)(2 * c + h2)) ^ sw) << 4)),
+                       "r"(w[4 * h2]), "r"(w[4 * h2 + 1]), "r"(w[4 * h2 + 2]), "r"(w[4 * h2 + 3])
+                       : "memory");
+        CB_GTRE(64 * ti + 42 + c);
+      }
+      // flush: lane = (row within a group of four, 16-byte unit), 8 lanes cover one 128-byte row of the tile
+      {
+        const int f_row = lane >> 3, f_u = lane & 7;
+        const int rows_left = p.M - row0 - f_row;  // row f_row + 4 it exists iff 4 it < rows_left
+        bf16* d = out16 + (long long)(row0 + f_row) * p.ldo + col0 + f_u * 8;
+        const long long f_step = 4 * p.ldo;
+        const bool ok = col0 + f_u * 8 < p.N;
+        const uint32_t f_src = stg + f_row * 128;
+        __syncwarp();
+        uint4 val[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it)  // row = 4 it + f_row: (row & 7) = 4 (it & 1) + f_row
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(val[it].x), "=r"(val[it].y), "=r"(val[it].z), "=r"(val[it].w)
+                       : "r"(f_src + it * 512 + (((uint32_t)f_u ^ (uint32_t)(4 * (it & 1) + f_row)) << 4)));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (ok && 4 * it < rows_left) *reinterpret_cast<uint4*>(d) = val[it];
+          d += f_step;
+        }
+        __syncwarp();  // the tile is rewritten by the next item
+      }
+      CB_GTRE(64 * ti + 50);
+#ifdef CB_GEMM_TRACE
+      ++ti;
+#endif
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    };
     const int mode = p.epi == CB_EPI_GELU ? 1 : (has_aux ? 2 : (p.out_fp32 ? (p.atomic_add ? 4 : 3) : 0));
+    // (`CB_GEMM_WIDE=0` -> GemmArgs::wide = 0 keeps everything on the narrow path for A/B measurements)
+    const bool wide = C::WIDE && p.wide != 0 && mode == 0 && !has_res && !has_out2 && !has_rs && p.colsum == nullptr;
     for (int item = worker; item < items; item += n_workers) {
+      if constexpr (C::WIDE) {
+        if (wide) {
+          run_tile_wide(item);
+          continue;
+        }
+      }
       switch (mode) {
         case 0: run_tile(std::integral_constant<int, 0>{}, item); break;
         case 1: run_tile(std::integral_constant<int, 1>{}, item); break;
@@ -577,6 +679,11 @@ extern "C" int cb_gemm_bf16(const void* A, long long lda, int a_mn_major, const 
   p.aux = reinterpret_cast<const bf16*>(aux), p.ldaux = ldaux;
   p.epi = epilogue, p.alpha = alpha, p.colsum = colsum;
   p.row_scale = row_scale, p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  static const int wide_ok = [] {
+    const char* e = getenv("CB_GEMM_WIDE");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  p.wide = wide_ok;
   CB_CHECK_ARG(row_scale == nullptr || (epilogue == CB_EPI_NONE && !accumulate && rows_per_group > 0),
                "gemm: row_scale needs the plain epilogue, a non-accumulating output and rows_per_group > 0");
   CB_CHECK_ARG(colsum == nullptr || (out_dtype == CB_DT_BF16 && epilogue != CB_EPI_GELU && !accumulate),
