@@ -97,8 +97,8 @@ def measured_peaks() -> tuple[dict, str]:
 
 def measured_write_gbs(dev) -> float:
     """HBM WRITE bandwidth, measured live: a 1 GiB fill (no reads), best of 6.  The copy figure of MEASURED_PEAKS.json counts
-    read + write bytes; a kernel that mostly writes (fc1 + GELU stores two bf16 outputs per accumulator element) is bounded
-    by this number instead (profiles/r02_gemm_epilogue.md)."""
+    read + write bytes; this pool's B200s fill at ~7.1 TB/s, so the written-bytes roof below has not bound any GEMM shape so
+    far (profiles/r02_gemm_epilogue.md records the hypothesis it was added to test)."""
     buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
     best = 0.0
     for i in range(7):
