@@ -24,6 +24,7 @@ def gemms():
         for bn in (0, 64, 128, 256):
             _C.gemm(a, b, torch.empty(m, n, device=DEV, dtype=BF), block_n=bn)
         bias, res = rn(n), rn(m, n)
+        _C.gemm(a, b, torch.empty(m, n, device=DEV, dtype=BF), bias=bias, block_n=256)  # wide-store epilogue when paired
         _C.gemm(a, b, res, out2=torch.empty(m, n, device=DEV, dtype=BF), bias=bias, residual=res)
         pre, act = torch.empty(m, n, device=DEV, dtype=BF), torch.empty(m, n, device=DEV, dtype=BF)
         _C.gemm(a, b, pre, out2=act, bias=bias, epilogue=_C.EPI_GELU)
@@ -58,6 +59,16 @@ def layernorm():
                          dgamma=torch.zeros(d, device=DEV), dbeta=torch.zeros(d, device=DEV))
 
 
+def input_pipeline():
+    for shape, ext in (((3, 1, 24, 20, 6), [[24, 20, 6], [17, 20, 5], [24, 13, 6]]), ((3, 1, 40, 36), [[40, 36, 1], [33, 36, 1], [40, 29, 1]])):
+        raw = torch.randint(0, 900, shape, device=DEV, dtype=torch.int16)
+        extent = torch.tensor(ext, dtype=torch.int32, device=DEV)
+        zoom = torch.tensor([1.0, 0.93, 1.08], device=DEV)
+        _C.zoom_intensity(raw, extent, zoom, torch.empty(shape, device=DEV))
+        flat = raw.reshape(3, -1).float()
+        _C.scale_intensity(raw, flat.min(1).values.contiguous(), flat.max(1).values.contiguous(), torch.empty(shape, device=DEV))
+
+
 def model_step():
     g = torch.load(ROOT / "tests" / "golden" / "mae_small_4view.pt")
     model = CineMA(**g["kw"]).to(DEV)
@@ -81,6 +92,7 @@ if __name__ == "__main__":
         attention()
     if "ln" in which:
         layernorm()
+        input_pipeline()
     if "model" in which:
         model_step()
     torch.cuda.synchronize()
