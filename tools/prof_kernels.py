@@ -83,6 +83,18 @@ def build(only):
         K.append(("colsum 10960x3072", mk(_C.colsum, xc, oc), 10960 * 3072 * 2, 0))
         xc2, oc2 = rn(32848, 512, dtype=BF), torch.zeros(512, device=DEV)
         K.append(("colsum 32848x512", mk(_C.colsum, xc2, oc2), 32848 * 512 * 2, 0))
+    if "misc" in only:  # input pipeline: RandZoom + ScaleIntensity + padding of one batch (SAX int16, LAX uint8)
+        for tag, shape, dt in (("sax 192x192x16", (B, 1, 192, 192, 16), torch.int16), ("lax 192x192", (B, 1, 192, 192), torch.uint8)):
+            raw = torch.randint(0, 255, shape, device=DEV, dtype=torch.int32).to(dt)
+            nd = len(shape) - 2
+            extent = torch.tensor([list(shape[2:]) + [1] * (3 - nd)] * B, dtype=torch.int32, device=DEV)
+            zoom = (0.9 + 0.2 * torch.rand(B, device=DEV)).contiguous()
+            out = torch.empty(shape, device=DEV)
+            keys = torch.empty(2 * B, dtype=torch.int32, device=DEV)
+            n = raw.numel()
+            K.append((f"zoom+scale+pad {tag}", mk(_C.zoom_intensity, raw, extent, zoom, out, keys), n * (raw.element_size() + 12), 0))
+            lo, hi = torch.zeros(B, device=DEV), torch.full((B,), 255.0, device=DEV)
+            K.append((f"scale_intensity {tag}", mk(_C.scale_intensity, raw, lo, hi, out), n * (raw.element_size() + 4), 0))
     if "dw" in only:
         grid, f, c, nk = (12, 12, 16), (4, 4, 1), 64, 576
         n = 12 * 12 * 16
