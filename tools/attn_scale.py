@@ -1,5 +1,8 @@
+"""Attention forward / backward time against the number of key tiles and query tiles (head_dim 32 and 64, B = 16): the
+slope gives the cost per 128 x 128 tile over the whole grid, the intercept the fixed cost per CTA
+(profiles/r01_attention_clock_trace.md).   python tools/attn_scale.py"""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parents[1]))
 from cinema_b200 import _C
 DEV='cuda'; BF=torch.bfloat16
 def run(nq, nk, h, d, B=16):
