@@ -37,6 +37,8 @@ _SIGNATURES = {
     "cb_scale_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "cb_zoom_intensity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                   c_void_p]),
+    "cb_seg_loss_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_seg_loss_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_gemm_bf16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                              c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
                              c_longlong, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -409,6 +411,39 @@ def zoom_intensity(raw: torch.Tensor, extent: torch.Tensor, zoom: torch.Tensor, 
     _check(lib().cb_zoom_intensity(_ptr(raw), _RAW_DT[raw.dtype], _ptr(extent), _ptr(zoom), _ptr(out), _ptr(keys_ws), b,
                                    len(size), sz, int(len(size) == 2), _stream()), "zoom_intensity")
     return out
+
+
+_LABEL_DT = {torch.int64: 0, torch.int32: 1, torch.int16: 2, torch.uint8: 3}
+
+
+def _seg_args(logits: torch.Tensor, labels: torch.Tensor):
+    assert logits.dtype in (torch.float32, torch.bfloat16) and logits.is_contiguous() and logits.dim() >= 3
+    b, c = logits.shape[0], logits.shape[1]
+    s = logits[0, 0].numel()
+    assert labels.dtype in _LABEL_DT and labels.is_contiguous() and labels.numel() == b * s, "labels: (B, 1, *spatial) integers"
+    return b, c, s, (DT_F32 if logits.dtype == torch.float32 else DT_BF16), _LABEL_DT[labels.dtype]
+
+
+def seg_loss_fwd(logits: torch.Tensor, labels: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """Cross-entropy (ignore_index -1) + foreground soft-Dice loss of channel-first logits (B, C, *spatial) against integer
+    labels (B, 1, *spatial): -> (out (3,) fp32 = [loss, cross-entropy, mean Dice loss], coef for :func:`seg_loss_bwd`)."""
+    b, c, s, ldt, ydt = _seg_args(logits, labels)
+    acc = torch.empty(b * c * 3 + 2, dtype=torch.float32, device=logits.device)
+    out = torch.empty(3, dtype=torch.float32, device=logits.device)
+    coef = torch.empty(b * c * 2 + 1, dtype=torch.float32, device=logits.device)
+    _check(lib().cb_seg_loss_fwd(_ptr(logits), ldt, _ptr(labels), ydt, b, c, s, _ptr(acc), _ptr(out), _ptr(coef), _stream()),
+           "seg_loss_fwd")
+    return out, coef
+
+
+def seg_loss_bwd(logits: torch.Tensor, labels: torch.Tensor, coef: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """d loss / d logits * grad_out (a one-element fp32 device tensor), in the logits' dtype and layout."""
+    b, c, s, ldt, ydt = _seg_args(logits, labels)
+    assert grad_out.dtype == torch.float32 and grad_out.numel() == 1 and coef.numel() == b * c * 2 + 1
+    dl = torch.empty_like(logits)
+    _check(lib().cb_seg_loss_bwd(_ptr(logits), ldt, _ptr(labels), ydt, b, c, s, _ptr(coef), _ptr(grad_out), _ptr(dl), _stream()),
+           "seg_loss_bwd")
+    return dl
 
 
 def mae_loss_finalize(acc: torch.Tensor, sq_count, patch_count, out: torch.Tensor, scales: torch.Tensor) -> None:

@@ -33,17 +33,14 @@ def regression_loss(preds: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
 
 
 def segmentation_loss(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
-    """Mean of soft Dice (foreground and background, softmax) and cross-entropy: the definition of MONAI's
-    ``DiceCELoss(include_background=True, to_onehot_y=True, softmax=True)`` used by cinema/segmentation/train.py:77-103."""
-    n_cls = logits.shape[1]
-    ce = F.cross_entropy(logits.float(), label.long())
-    prob = logits.float().softmax(dim=1)
-    onehot = F.one_hot(label.long(), n_cls).movedim(-1, 1).to(prob.dtype)
-    dims = tuple(range(2, prob.dim()))
-    inter = (prob * onehot).sum(dims)
-    denom = prob.sum(dims) + onehot.sum(dims)
-    dice = 1.0 - (2.0 * inter + 1e-5) / (denom + 1e-5)
-    return dice.mean() + ce
+    """Cross-entropy (``ignore_index=-1``) + MONAI ``DiceLoss(include_background=False, softmax=True)``, the loss of
+    cinema/segmentation/train.py:77-103 and cinema/examples/train/segmentation.py:238-242, through the fused forward / backward
+    kernels (``cinema_b200.segmentation.loss``).  ``label``: (B, *spatial) or (B, 1, *spatial) integers, -1 = unlabelled."""
+    from cinema_b200.segmentation.loss import segmentation_loss as fused
+
+    if label.dim() == logits.dim() - 1:
+        label = label.unsqueeze(1)
+    return fused(logits, label)[0]
 
 
 def finetune_one_epoch(model: nn.Module, batches: Iterable[tuple[dict[str, torch.Tensor], torch.Tensor]],

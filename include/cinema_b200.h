@@ -248,6 +248,16 @@ int cb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, long 
  * in the tail of its predecessor. */
 int cb_set_pdl(int enabled);
 
+/* Segmentation loss of the fine-tuning scripts (cinema/segmentation/train.py:77-103): F.cross_entropy(ignore_index = -1) +
+ * MONAI DiceLoss(include_background=False, softmax=True) over channel-first logits (B, C, S = prod(spatial)), 2 <= C <= 8,
+ * logits fp32 or bf16, labels (B, S) of label_dtype 0 int64 / 1 int32 / 2 int16 / 3 uint8 (-1 = unlabelled: no cross-entropy
+ * term, background for the Dice term).  Forward: one pass + a one-block finalize.  acc: (B * C * 3 + 2) fp32 scratch (zeroed
+ * here); out[0..2] = loss, cross-entropy, mean Dice loss; coef: (B * C * 2 + 1) fp32 kept for the backward.  Backward: one pass,
+ * dlogits (same dtype / layout as logits) = grad_out[0] * d loss / d logits. */
+int cb_seg_loss_fwd(const void* logits, int logits_dtype, const void* labels, int label_dtype, int B, int C, long long S,
+                    float* acc, float* out, float* coef, void* stream);
+int cb_seg_loss_bwd(const void* logits, int logits_dtype, const void* labels, int label_dtype, int B, int C, long long S,
+                    const float* coef, const float* grad_out, void* dlogits, void* stream);
 /* Diagnostics: register a DEVICE buffer of at least 1024 long long (or NULL to switch off, the default).  While set, one
  * CTA in the middle of the grid of every second-generation attention launch stamps clock64() at the phase boundaries of
  * its softmax / compute warps and of its MMA-issuing warp (slot layout and reader: tools/attn_trace.py).  This is how

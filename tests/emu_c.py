@@ -407,6 +407,36 @@ def adamw_flat(p, g, m, v, p16, hyper, beta1, beta2, eps, weight_decay, gnorm_sq
         p16.copy_(p.to(BF16))
 
 
+def _seg_restated(logits, labels):
+    import torch.nn.functional as F
+
+    lg = logits.float()
+    lab = labels.reshape(lg.shape[0], *lg.shape[2:]).long()
+    n_cls = lg.shape[1]
+    ce = F.cross_entropy(lg, lab, ignore_index=-1)
+    onehot = F.one_hot(lab.clamp(min=0), n_cls).movedim(-1, 1).to(lg.dtype)
+    prob = lg.softmax(dim=1)
+    dims = tuple(range(2, lg.dim()))
+    inter = (prob[:, 1:] * onehot[:, 1:]).sum(dims)
+    denom = prob[:, 1:].sum(dims) + onehot[:, 1:].sum(dims)
+    dice = (1.0 - (2.0 * inter + 1e-5) / (denom + 1e-5)).mean()
+    return ce, dice
+
+
+def seg_loss_fwd(logits, labels):
+    ce, dice = _seg_restated(logits.detach(), labels)
+    b, c = logits.shape[:2]
+    return torch.stack([ce + dice, ce, dice]).float(), torch.zeros(b * c * 2 + 1)
+
+
+def seg_loss_bwd(logits, labels, coef, grad_out):
+    with torch.enable_grad():  # (called from inside an autograd backward, where grad mode is off)
+        lg = logits.detach().float().requires_grad_(True)
+        ce, dice = _seg_restated(lg, labels)
+        (g,) = torch.autograd.grad(ce + dice, lg)
+    return (g * grad_out.reshape(())).to(logits.dtype)
+
+
 def device_info():
     return 148, 10, 0
 
@@ -415,5 +445,5 @@ ALL = [
     "conv_gemm",
     "gemm", "colsum", "attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "cast_bf16", "mask_to_index",
     "gather_rows", "scatter_rows", "embed_rows", "colsum_seg", "scale_cast", "mae_loss_finalize", "patchify",
-    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "rope_apply", "sumsq", "adamw_flat", "expand_token_index", "dwconv_tokens", "dwconv_tokens_wgrad",
+    "gather_patches", "scatter_patches", "masked_mse_fwd", "device_info", "seg_loss_fwd", "seg_loss_bwd", "rope_apply", "sumsq", "adamw_flat", "expand_token_index", "dwconv_tokens", "dwconv_tokens_wgrad",
 ]

@@ -295,8 +295,9 @@ def test_finetune_loop_with_layerwise_lr_decay(golden_dir, emulated_kernels):
     assert all(torch.isfinite(p).all() for p in model.parameters())
 
 
-def test_segmentation_loss_definition():
-    """Soft Dice + CE: perfect one-hot logits -> ~0, uniform logits -> (1 - 2/(1+C))-ish Dice + log C cross-entropy."""
+def test_segmentation_loss_definition(emulated_kernels):
+    """Foreground soft Dice + CE (cinema/segmentation/train.py:77-103): perfect one-hot logits -> ~0, uniform logits -> the
+    hand-computed Dice of classes 1.. + log C cross-entropy."""
     from cinema_b200.examples import finetune as ft
 
     label = torch.randint(0, 3, (2, 6, 6, 4))
@@ -305,7 +306,7 @@ def test_segmentation_loss_definition():
     uniform = torch.zeros(2, 3, 6, 6, 4)
     dice = []
     for b in range(2):  # per sample and class: 1 - (2 * n_c / 3) / (144 / 3 + n_c), probabilities are 1/3 everywhere
-        for c in range(3):
+        for c in range(1, 3):  # include_background=False
             n_c = float((label[b] == c).sum())
             dice.append(1.0 - (2.0 * n_c / 3 + 1e-5) / (144 / 3 + n_c + 1e-5))
     want = math.log(3) + sum(dice) / len(dice)

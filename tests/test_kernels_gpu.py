@@ -654,3 +654,32 @@ def test_zoom_intensity_kernel(dtype, nd):
         if j != 5:
             assert float(inside.min()) == 0.0 and float(inside.max()) == pytest.approx(1.0, abs=1e-6)
     assert float(out[5].abs().max()) == 0.0  # a constant frame (not zoomed) maps to 0
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 48, 40, 6), (3, 4, 64, 56), (1, 2, 33, 17), (2, 8, 20, 20, 4)])
+@pytest.mark.parametrize("logit_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.int16, torch.uint8])
+def test_seg_loss_kernels(shape, logit_dtype, label_dtype):
+    """cb_seg_loss_fwd / _bwd (cross-entropy with ignore_index -1 + foreground soft Dice, cinema/segmentation/train.py:77-103)
+    against the torch restatement on the same device: loss, both metrics and d loss / d logits (scaled by an upstream
+    gradient); unlabelled voxels with signed label types, every class count up to 8."""
+    from cinema_b200.segmentation.loss import segmentation_loss, segmentation_loss_restated
+
+    g = torch.Generator().manual_seed(11)
+    logits = (torch.randn(shape, generator=g) * 2.5).to(logit_dtype).to(DEV)
+    labels = torch.randint(0, shape[1], (shape[0], 1, *shape[2:]), generator=g)
+    if label_dtype != torch.uint8:
+        labels[torch.rand(labels.shape, generator=g) < 0.15] = -1
+    labels = labels.to(label_dtype).to(DEV)
+    x = logits.clone().requires_grad_(True)
+    loss, metrics = segmentation_loss(x, labels)
+    (loss * 1.7).backward()
+    ref_x = logits.float().clone().requires_grad_(True)
+    ref_loss, ref_ce, ref_dice = segmentation_loss_restated(ref_x, labels)
+    (ref_loss * 1.7).backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-5 * abs(float(ref_loss))
+    assert abs(float(metrics["cross_entropy"]) - float(ref_ce)) < 2e-5 * abs(float(ref_ce))
+    assert abs(float(metrics["mean_dice_loss"]) - float(ref_dice)) < 2e-5
+    tol = 1e-5 if logit_dtype == torch.float32 else 6e-3  # the gradient is stored in the logits' dtype
+    assert rel_err(x.grad.float(), ref_x.grad) < tol
+    assert x.grad.dtype == logit_dtype
