@@ -67,6 +67,11 @@ def input_pipeline():
         _C.zoom_intensity(raw, extent, zoom, torch.empty(shape, device=DEV))
         flat = raw.reshape(3, -1).float()
         _C.scale_intensity(raw, flat.min(1).values.contiguous(), flat.max(1).values.contiguous(), torch.empty(shape, device=DEV))
+    for dt in (torch.float32, BF):  # segmentation loss, forward + backward
+        logits = rn(2, 4, 24, 20, 6, dtype=dt)
+        labels = torch.randint(-1, 4, (2, 1, 24, 20, 6), device=DEV)
+        out, coef = _C.seg_loss_fwd(logits, labels)
+        _C.seg_loss_bwd(logits, labels, coef, torch.ones(1, device=DEV))
 
 
 def model_step():
