@@ -64,9 +64,13 @@ def main() -> None:
     seg = ConvUNetR(**seg_kw, channels_last=bool(a.channels_last)).to(DEV).train()
     y = torch.randint(0, 4, (b, 192, 192, 16), device=DEV)
 
-    def ours_seg():
+    from cinema_b200.segmentation.loss import segmentation_loss, segmentation_loss_restated
+
+    y1 = y.unsqueeze(1)
+
+    def ours_seg():  # the reference's loss (cross-entropy + foreground Dice, cinema/segmentation/train.py:77-103), fused kernels
         seg.zero_grad(set_to_none=True)
-        torch.nn.functional.cross_entropy(seg(x)["sax"].float(), y).backward()
+        segmentation_loss(seg(x)["sax"], y1)[0].backward()
 
     cfg = O.convunetr_config({k: v for k, v in seg_kw.items()})
     params = {k: v.detach().clone().requires_grad_(not k.endswith("pos_embed")) for k, v in seg.state_dict().items()}
@@ -76,7 +80,7 @@ def main() -> None:
             p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = O.convunetr_forward(params, cfg, x, seg.n_layers_wo_skip)["sax"]
-        torch.nn.functional.cross_entropy(logits.float(), y).backward()
+        segmentation_loss_restated(logits, y1)[0].backward()  # the same loss as torch ops (what the stock script runs)
 
     t_ours, t_stock = timed(ours_seg, a.steps, a.warmup), timed(stock_seg, a.steps, a.warmup)
     out["convunetr_acdc"] = {"ours_ms": round(t_ours, 2), "stock_torch_ms": round(t_stock, 2),
