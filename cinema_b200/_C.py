@@ -220,7 +220,8 @@ def conv_gemm(x_rows: torch.Tensor, w_taps: torch.Tensor, out: torch.Tensor, row
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == c_out
     _check(lib().cb_conv_gemm_bf16(_ptr(x_rows), ldx, rows, c_in, _ptr(w_taps), ldw, c_out, n_taps, _ints(row_off), _ptr(out), ldo,
-                                   out_dt, _ptr(bias), _ptr(residual), ldr, block_n, _stream()), "conv_gemm")
+                                   out_dt, _ptr(bias), _ptr(residual), ldr, block_n, _stream()),
+           f"conv_gemm (x {tuple(x_rows.shape)}, w {tuple(w_taps.shape)}, out {tuple(out.shape)})")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:

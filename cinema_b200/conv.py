@@ -247,6 +247,11 @@ class ConvTranspose3d(nn.ConvTranspose3d):
         self.grad_ckpt = enable
 
 
+# narrowest layer the opt-in GEMM convolution takes (CB_NATIVE_CONV_MIN_C for measurements; 32-channel layers work -- padded to
+# 64 on both sides -- but measured slower than cuDNN at full resolution, tools/bench_finetune.py)
+_NATIVE_MIN_C = int(__import__("os").environ.get("CB_NATIVE_CONV_MIN_C", "64"))
+
+
 class ConvResBlock(nn.Module):
     """x -> conv2(drop(act(norm2(conv1(act(norm1 x)))))) + shortcut(x)  (cinema/conv.py:276-346): the residual unit of
     the segmentation decoder.  Dense k x k (x k) convolutions at up to full image resolution: cuDNN under bf16 autocast."""
@@ -276,7 +281,39 @@ class ConvResBlock(nn.Module):
         if hasattr(self.shortcut, "set_grad_ckpt"):
             self.shortcut.set_grad_ckpt(enable)
 
+    native = False  # opt-in (ConvUNetR.set_native_convs): the two k^n convolutions on the tcgen05 GEMM instead of cuDNN
+    _spaces: dict | None = None
+
+    def _native_ok(self, x: torch.Tensor) -> bool:
+        if not (self.native and x.is_cuda and x.dim() in (4, 5)):
+            return False
+        for conv in (self.conv1, self.conv2):
+            if (tuple(conv.kernel_size) != (3,) * (x.dim() - 2) or tuple(conv.stride) != (1,) * (x.dim() - 2)
+                    or tuple(conv.dilation) != (1,) * (x.dim() - 2) or conv.groups != 1 or conv.padding != "same"
+                    or conv.in_channels < _NATIVE_MIN_C or conv.out_channels < _NATIVE_MIN_C or conv.out_channels % 8 != 0):
+                return False  # (narrow layers would be zero-padded to 64 channels on both sides: left to cuDNN)
+        return True
+
+    def _space(self, x: torch.Tensor):
+        from cinema_b200.conv_gemm import RowSpace
+
+        key = (x.shape[0], tuple(x.shape[2:]))
+        if self._spaces is None:
+            self._spaces = {}
+        if key not in self._spaces:
+            if len(self._spaces) > 8:
+                self._spaces.clear()
+            self._spaces[key] = RowSpace(*key)
+        return self._spaces[key]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._native_ok(x):
+            from cinema_b200.conv_gemm import conv3x3_dense
+
+            space = self._space(x)
+            h = conv3x3_dense(self.act(self.norm1(x)), self.conv1.weight, self.conv1.bias, space)
+            h = conv3x3_dense(self.dropout(self.act(self.norm2(h))), self.conv2.weight, self.conv2.bias, space)
+            return h + self.shortcut(x)
         h = self.conv1(self.act(self.norm1(x)))
         h = self.conv2(self.dropout(self.act(self.norm2(h))))
         return h + self.shortcut(x)

@@ -1,7 +1,8 @@
-"""EXPERIMENTAL: 3^n "same" convolution on the tcgen05 GEMM pipeline -- the building block for the
-native UNETR decoder of the next round.  Not used by any model yet; the kernel entry point (``cb_conv_gemm_bf16``) has not
-been validated on a GPU in round 1.  The arithmetic is pinned on the CPU (``tools/conv_rowspace_prototype.py``) and this
-host logic is exercised through the emulated kernels (``tests/test_conv_gemm_host.py``).
+"""3^n "same" convolution on the tcgen05 GEMM pipeline.  The kernel entry point
+(``cb_conv_gemm_bf16``) is validated on the B200 against ``F.conv2d / conv3d`` (``tests/test_conv_gemm_gpu.py``), the
+arithmetic is pinned on the CPU (``tools/conv_rowspace_prototype.py``) and this host logic is exercised through the emulated
+kernels (``tests/test_conv_gemm_host.py``).  ``ConvResBlock`` (the residual unit of the UNETR decoder) uses it when its
+``native`` switch is on (``ConvUNetR.set_native_convs``, opt-in).
 
 Feature maps live in a zero-haloed channel-last ROW SPACE: a (B, C, *S) map is the matrix X[B * prod(S + 2), C] (bf16).
 ``RowSpace`` owns the geometry (tap offsets, interior mask, guard rows); ``Conv3x3Fn`` is the autograd function:
@@ -51,12 +52,14 @@ class RowSpace:
             self._mask[key] = m.reshape(-1, 1)
         return self._mask[key]
 
-    def to_rows(self, x: torch.Tensor) -> torch.Tensor:
-        """(B, C, *S) any float dtype -> guarded row-space storage; returns the (rows, C) bf16 view between the guards."""
+    def to_rows(self, x: torch.Tensor, channels: int | None = None) -> torch.Tensor:
+        """(B, C, *S) any float dtype -> guarded row-space storage; returns the (rows, C) bf16 view between the guards.
+        ``channels`` > C pads the channel axis with zeros (the GEMM needs C_in in multiples of 64)."""
         c = x.shape[1]
-        store = torch.zeros((self.rows + 2 * self.guard, c), dtype=BF16, device=x.device)
-        body = store[self.guard:self.guard + self.rows].view(self.batch, *self.padded, c)
-        body[(slice(None), *[slice(1, s + 1) for s in self.spatial])] = x.movedim(1, -1).to(BF16)
+        cp = c if channels is None else channels
+        store = torch.zeros((self.rows + 2 * self.guard, cp), dtype=BF16, device=x.device)
+        body = store[self.guard:self.guard + self.rows].view(self.batch, *self.padded, cp)
+        body[(slice(None), *[slice(1, s + 1) for s in self.spatial], slice(0, c))] = x.movedim(1, -1).to(BF16)
         return store[self.guard:self.guard + self.rows]
 
     def from_rows(self, rows: torch.Tensor) -> torch.Tensor:
@@ -138,3 +141,20 @@ def conv3x3(x_rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | Non
     if x_rows.shape != (space.rows, weight.shape[1]):
         raise ValueError(f"x_rows {tuple(x_rows.shape)} does not match the row space ({space.rows}, {weight.shape[1]})")
     return Conv3x3Fn.apply(x_rows, weight, bias, space, skip32)
+
+
+def conv3x3_dense(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, space: RowSpace) -> torch.Tensor:
+    """(B, C_in, *S) feature map -> (B, C_out, *S) bf16 (a channel-last strided VIEW of the haloed output rows): the same
+    contract as ``F.conv{2,3}d(x, weight, bias, padding="same")`` under bf16 autocast.  C_in that is not a multiple of 64 is
+    zero-padded to one (activations and weights; the wasted k-blocks are the price of the 128B-swizzled operand tiles), and
+    so is C_out (zero filters whose outputs are sliced away: the output gradient then has the width the dgrad GEMM needs)."""
+    import torch.nn.functional as F
+
+    c_out, c_in = weight.shape[:2]
+    cp, cop = (c_in + 63) // 64 * 64, (c_out + 63) // 64 * 64
+    if cp != c_in or cop != c_out:  # (C_out too: it is the contraction width of the dgrad GEMM)
+        weight = F.pad(weight, (0, 0) * (weight.dim() - 2) + (0, cp - c_in, 0, cop - c_out))
+        if bias is not None and cop != c_out:
+            bias = F.pad(bias, (0, cop - c_out))
+    y = space.from_rows(conv3x3(space.to_rows(x, cp), weight, bias, space))
+    return y[:, :c_out] if cop != c_out else y

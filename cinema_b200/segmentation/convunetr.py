@@ -217,6 +217,15 @@ class ConvUNetR(nn.Module):
             if isinstance(m, ConvLayerNorm):
                 m.keep_channels_last = enable
 
+    def set_native_convs(self, enable: bool = True) -> None:
+        """Opt-in: every ``ConvResBlock`` of the skip blocks and of the UNETR decoder whose 3^n convolutions have at least 32
+        input channels runs them as K-concatenated tcgen05 GEMMs over a zero-haloed channel-last row space
+        (``cinema_b200.conv_gemm``) instead of cuDNN; the others, the dense stem and the transposed convolutions stay on
+        cuDNN.  Values match the cuDNN path to bf16 rounding; state dict and shapes are unaffected."""
+        for m in self.modules():
+            if isinstance(m, ConvResBlock):
+                m.native = enable
+
     @torch.jit.ignore
     def set_grad_ckpt(self, enable: bool = True) -> None:
         """API compatibility (cinema/segmentation/convunetr.py:421-434); activations are kept, not recomputed."""

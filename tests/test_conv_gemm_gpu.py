@@ -1,17 +1,12 @@
-"""GPU checks of the EXPERIMENTAL GEMM convolution (cb_conv_gemm_bf16, cinema_b200/conv_gemm.py).  The kernel variant was
-written at the end of round 1 after the GPU budget was spent, so these tests are opt-in until it has been validated:
-
-    CB_EXPERIMENTAL_CONV=1 python -m pytest tests/test_conv_gemm_gpu.py -m gpu -q
-"""
-
-import os
+"""GPU checks of the GEMM convolution (cb_conv_gemm_bf16, cinema_b200/conv_gemm.py): the kernel entry point with its
+autograd function against F.conv2d / conv3d, and the opt-in ``native`` switch of ConvResBlock against its cuDNN path.  (Opt-in
+behind CB_EXPERIMENTAL_CONV=1 until the kernel was validated on the B200 in round 2; part of the default GPU run since.)"""
 
 import pytest
 import torch
 import torch.nn.functional as F  # noqa: N812
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CB_EXPERIMENTAL_CONV") != "1", reason="experimental kernel: opt in with CB_EXPERIMENTAL_CONV=1")]
+pytestmark = [pytest.mark.gpu]
 
 DEV = "cuda"
 
@@ -50,3 +45,32 @@ def test_conv_gemm_kernel_against_torch(spatial, cin, cout):
     assert rel(space.from_rows(x_rows.grad), xr.grad) < 1e-2
     assert rel(w.grad, w_ref.grad) < 1e-2
     assert rel(bias.grad, b_ref.grad) < 1e-2
+
+
+@pytest.mark.parametrize(("nd", "cin", "cout", "shape"), [(3, 64, 64, (2, 64, 24, 20, 6)), (3, 128, 64, (1, 128, 12, 12, 8)),
+                                                            (2, 96, 40, (2, 96, 30, 28)), (3, 32, 32, (1, 32, 16, 16, 4))])
+def test_conv_res_block_native_switch_against_cudnn(nd, cin, cout, shape, monkeypatch):
+    """``ConvResBlock.native`` (ConvUNetR.set_native_convs): both 3^n convolutions as K-concatenated GEMMs over the haloed row
+    space -- channel counts that are not multiples of 64 are zero-padded on both sides -- against the same block on cuDNN under
+    bf16 autocast: output, input gradient, weight and bias gradients within bf16 rounding of each other."""
+    from cinema_b200 import conv as C
+
+    monkeypatch.setattr(C, "_NATIVE_MIN_C", 32)
+    torch.manual_seed(0)
+    blk = C.ConvResBlock(n_dims=nd, in_chans=cin, out_chans=cout, norm="layer").to(DEV)
+    x = torch.randn(shape, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = blk(x).float()
+    ref.square().mean().backward()
+    want = [x.grad.clone(), blk.conv1.weight.grad.clone(), blk.conv2.weight.grad.clone(), blk.conv2.bias.grad.clone()]
+    x.grad = None
+    blk.zero_grad()
+    blk.native = True
+    assert blk._native_ok(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = blk(x).float()
+    out.square().mean().backward()
+    got = [x.grad, blk.conv1.weight.grad, blk.conv2.weight.grad, blk.conv2.bias.grad]
+    assert rel(out, ref) < 1e-2
+    for g, w in zip(got, want):
+        assert rel(g, w) < 2.5e-2

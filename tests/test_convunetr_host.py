@@ -144,3 +144,29 @@ def test_reference_multi_view_convunetr(emulated_kernels):
     assert out["lax"].shape == (2, 3, 16, 16) and out["sax"].shape == (2, 3, 16, 24, 16)
     sum(v.sum() for v in out.values()).backward()
     assert unetr.encoder.cls_token.grad is None or bool(torch.isfinite(unetr.encoder.cls_token.grad).all())
+
+
+def test_native_conv_switch_matches_the_cudnn_path(emulated_kernels, monkeypatch):
+    """``ConvUNetR.set_native_convs``: the ConvResBlock convolutions with >= 32 input channels as K-concatenated GEMMs over the
+    zero-haloed row space (channels padded to a multiple of 64) give the torch convolution's values to bf16 rounding, forward and
+    backward; blocks with fewer input channels (the image block) stay on the torch path."""
+    from cinema_b200.conv import ConvResBlock
+
+    torch.manual_seed(0)
+    monkeypatch.setattr(ConvResBlock, "_native_ok", lambda self, x: self.native and self.conv1.in_channels >= 32
+                        and self.conv1.padding == "same" and tuple(self.conv1.kernel_size) == (3,) * (x.dim() - 2))
+    for nd, cin, cout, shape in ((3, 64, 64, (2, 64, 5, 6, 4)), (2, 32, 32, (2, 32, 7, 6)), (3, 96, 40, (1, 96, 4, 4, 3))):
+        blk = ConvResBlock(n_dims=nd, in_chans=cin, out_chans=cout, norm="layer")
+        x = torch.randn(shape, requires_grad=True)
+        ref = blk(x)
+        ref.square().sum().backward()
+        want = [x.grad.clone(), blk.conv1.weight.grad.clone(), blk.conv2.bias.grad.clone()]
+        x.grad = None
+        blk.zero_grad()
+        blk.native = True
+        out = blk(x)
+        out.square().sum().backward()
+        got = [x.grad, blk.conv1.weight.grad, blk.conv2.bias.grad]
+        assert float((out - ref).norm() / ref.norm()) < 6e-3
+        for g, w in zip(got, want):
+            assert float((g - w).norm() / w.norm()) < 1.5e-2

@@ -83,6 +83,23 @@ def main() -> None:
         segmentation_loss_restated(logits, y1)[0].backward()  # the same loss as torch ops (what the stock script runs)
 
     t_ours, t_stock = timed(ours_seg, a.steps, a.warmup), timed(stock_seg, a.steps, a.warmup)
+    # opt-in: the ConvResBlock convolutions with >= 32 input channels as tcgen05 GEMMs (ConvUNetR.set_native_convs)
+    seg.set_native_convs(True)
+    try:
+        ref_logits = None
+        seg.set_native_convs(False)
+        with torch.no_grad():
+            ref_logits = seg(x)["sax"].float()
+        seg.set_native_convs(True)
+        with torch.no_grad():
+            nat_logits = seg(x)["sax"].float()
+        rel = float((nat_logits - ref_logits).norm() / ref_logits.norm())
+        t_nat = timed(ours_seg, a.steps, a.warmup)
+        out["convunetr_acdc_native_convs"] = {"ours_ms": round(t_nat, 2), "speedup_vs_stock": round(t_stock / t_nat, 2),
+                                              "logits_rel_l2_vs_cudnn_path": rel}
+    except Exception as exc:  # noqa: BLE001 -- the opt-in path must not take the benchmark down
+        out["convunetr_acdc_native_convs"] = {"error": repr(exc)[:300]}
+    seg.set_native_convs(False)
     out["convunetr_acdc"] = {"ours_ms": round(t_ours, 2), "stock_torch_ms": round(t_stock, 2),
                              "ours_volumes_per_s": round(b / t_ours * 1e3, 1), "stock_volumes_per_s": round(b / t_stock * 1e3, 1),
                              "speedup": round(t_stock / t_ours, 2)}

@@ -2,7 +2,7 @@
 # Round-2 GPU call C: tests, synccheck of the attention kernels, quick bench (replayed kernel table), GEMM timings and an
 # ncu --set full capture of the GEMM shapes (source-level, for the epilogue analysis).
 mkdir -p gpurun_out
-( CB_EXPERIMENTAL_CONV=1 timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
+( timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 TOOLS="synccheck" TARGETS="attn,gemm" SAN_TIMEOUT=200 bash tools/gpu_sanitize.sh
 ( timeout 600 python bench.py --steps 10 --warmup 3 --no-stock-gpu --no-cpu-baseline 2>&1 | tail -2 ) > gpurun_out/bench_c2.log

@@ -3,7 +3,7 @@
 # ncu launch list of one eager step, compute-sanitizer.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-( CB_EXPERIMENTAL_CONV=1 timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
+( timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
 ( timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ) > gpurun_out/smoke.log
 ( timeout 600 python bench.py --steps 30 --warmup 5 2>&1 | tail -2 ) > gpurun_out/bench_base.log
 ( timeout 600 python bench.py --steps 10 --warmup 3 --size large --lax 256 --no-cpu-baseline 2>&1 | tail -2 ) > gpurun_out/bench_large256.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU call J: wide-store epilogue for plain bf16 outputs -- full GPU tests, step A/B against the narrow path (same box).
 mkdir -p gpurun_out
-( CB_EXPERIMENTAL_CONV=1 timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -6 ) > gpurun_out/pytest_gpu.log
+( timeout 600 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -6 ) > gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 for W in 1 0 1 0; do
   echo "== CB_GEMM_WIDE=$W"
