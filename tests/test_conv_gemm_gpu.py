@@ -13,7 +13,7 @@ DEV = "cuda"
 
 def rel(a, b):
     a, b = a.double().cpu(), b.double().cpu()
-    return float((a - b).norm() / (b.norm() + 1e-30))
+    return float(((a - b).norm() / (b.norm() + 1e-30)).detach())
 
 
 @pytest.mark.parametrize(("spatial", "cin", "cout"), [((12, 12, 16), 512, 512), ((24, 24, 16), 256, 256), ((48, 48, 16), 64, 64),
