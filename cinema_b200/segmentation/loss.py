@@ -31,12 +31,10 @@ class _SegLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):  # type: ignore[override]
         logits, labels, coef = ctx.saved_tensors
-        # out = [loss, ce, dice] with loss = ce + dice: the gradient of any combination is (g0 + g1) d ce + (g0 + g2) d dice;
-        # the kernel differentiates the SUM, which is what the training loop uses -- separate weights are not supported
-        g = grad_out.to(torch.float32)
-        if bool((g[1:] != 0).any()):
-            raise NotImplementedError("segmentation_loss: differentiate the total loss (out[0]); the metrics are detached")
-        return _C.seg_loss_bwd(logits, labels, coef, g[:1].contiguous()), None
+        # out = [loss, ce, dice]: only out[0] (= ce + dice, what the training loop minimises) is differentiable here --
+        # ``segmentation_loss`` hands the other two out detached, so their incoming gradient is zero by construction (it is
+        # not inspected: that would be a device-to-host sync in every backward)
+        return _C.seg_loss_bwd(logits, labels, coef, grad_out.to(torch.float32)[:1].contiguous()), None
 
 
 def segmentation_loss(logits: torch.Tensor, labels: torch.Tensor) -> tuple[torch.Tensor, dict[str, torch.Tensor]]:
