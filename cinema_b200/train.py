@@ -238,6 +238,7 @@ class MAETrainer:
         self._copy_stream = None
         self._staged = None
         self._staged_free = None
+        self.prefetch_misses = 0  # step() calls that found a prefetched batch other than the one they were given
         self._g_fb = self._g_opt = None
         self._fb_segments: list = []  # [(graph, flat ranges to all-reduce once it has run)] when the capture is split
         self._capturing = False
@@ -268,6 +269,11 @@ class MAETrainer:
                 self._inputs[k].copy_(v, non_blocking=True)
             self._staged_free.record(torch.cuda.current_stream(dev))
             return
+        if self._prefetched is not None:
+            # a DIFFERENT batch than the prefetched one: the staged copy is dropped (the hand-off is by object identity, as a
+            # loader that yields each pinned batch once would use it) and this batch takes the in-line upload below
+            self._prefetched = None
+            self.prefetch_misses += 1
         for k, v in batch.items():
             self._inputs[k].copy_(v, non_blocking=True)
 
