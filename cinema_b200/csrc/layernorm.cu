@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) ln_fwd_small_kernel(const float* __restri
 }
 
 template <int LPR, int UNR, bool DY_BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)  // <= 128 registers: two blocks (16 warps) per SM; at 151 registers only one was resident
 ln_bwd_small_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
                     const float* __restrict__ mean_i, const float* __restrict__ rstd_i, const float* __restrict__ gamma,
                     const float* __restrict__ dres, long long lddres, int M, float* __restrict__ dx32, long long lddx32,
