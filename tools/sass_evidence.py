@@ -15,7 +15,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 PATTERNS = OrderedDict([
     ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA\b"), ("LDTM (tcgen05.ld)", r"\bLDTM\b"), ("STTM (tcgen05.st)", r"\bSTTM\b"),
-    ("UTMALDG (TMA tensor load)", r"\bUTMALDG\b"), ("UBLKCP (bulk copy)", r"\bUBLKCP\b"), ("UTMAPF / prefetch", r"\bUTMAPF\b"),
+    ("UTMALDG (TMA tensor load)", r"\bUTMALDG\b"), ("UBLKCP (bulk copy)", r"\bUBLKCP\b"),
+    ("UTMAREDG / UBLKRED (bulk reduce-add)", r"\b(UTMAREDG|UBLKRED)\b"), ("UTMACCTL.PF (descriptor prefetch)", r"\bUTMACCTL\b"),
     ("SYNCS (mbarrier)", r"\bSYNCS\b"), ("RED / ATOM", r"\b(RED|ATOMG?|REDG)\b"), ("MUFU.EX2", r"\bMUFU\.EX2\b"),
     ("HMMA (legacy, must be 0)", r"\bHMMA\b"),
 ])
@@ -45,9 +46,11 @@ def main() -> None:
         name = re.sub(r"^void ", "", name).split("(")[0]
         rows.append((name, n_inst, [len(re.findall(p, body)) for p in PATTERNS.values()]))
     rows.sort(key=lambda r: -r[1])
-    out = ["# r01: SASS evidence (cuobjdump -sass of libcinema_b200.so, sm_100a)", "",
+    tag = Path(a.out).name.split("_")[0] if a.out else "build"
+    out = [f"# {tag}: SASS evidence (cuobjdump -sass of libcinema_b200.so, sm_100a)", "",
            "Counts of instructions per kernel.  `UTC*MMA` = tcgen05.mma, `LDTM` / `STTM` = tcgen05.ld / st (TMEM), `UTMALDG` = TMA "
-           "tensor load, `UBLKCP` = cp.async.bulk, `SYNCS` = mbarrier operations.  No kernel contains the legacy `HMMA` path.", "",
+           "tensor load, `UBLKCP` = cp.async.bulk, `UTMAREDG` / `UBLKRED` = cp.reduce.async.bulk (tensor / linear reduce-add), "
+           "`SYNCS` = mbarrier operations.  No kernel contains the legacy `HMMA` path.", "",
            "| kernel | SASS instructions | " + " | ".join(PATTERNS) + " |", "|---|---:|" + "---:|" * len(PATTERNS)]
     for name, n_inst, counts in rows:
         out.append(f"| `{name[:90]}` | {n_inst} | " + " | ".join(str(c) for c in counts) + " |")
